@@ -1,0 +1,366 @@
+// K7 — ConjugateGradient::solve (linearsolver.rs:27-61) as three fused kernels per iteration with
+// every scalar (alpha, beta, r.r, the stop test) kept on the device:
+//
+//   A  ap = A p,  pAp = p.ap                    SpMV with the dot fused into its epilogue (spmv.cu)
+//   B  x += (p*alpha); r -= (ap*alpha); rr' = r.r    alpha = rr / pAp computed by every thread
+//   C  stop test sqrt(rr') < threshold; p = (p*beta) + r   beta = rr' / rr
+//
+// Elementwise arithmetic is the reference's: product rounded, then add (two roundings, never an FMA),
+// alpha/beta are divisions in T.  Only the two reductions are re-ordered (fixed-order tree in f64).
+// Algorithmic bytes per iteration: SpMV bytes + 9*N*sizeof(T)  (B: x,p,r,ap in, x,r out; C: r,p in, p out)
+// against ~24*N*sizeof(T) plus 3-4 allocations in the reference's clone-heavy loop.
+//
+// Iterations are replayed from a CUDA graph in batches; the host only polls a pinned copy of the
+// (iteration, done) pair one batch behind the GPU, so the device never waits for the CPU.  After the
+// stop test fires the remaining kernels of a batch exit immediately, leaving x, r, p untouched — the
+// reference's `break` (linearsolver.rs:52-54).
+#include "common.cuh"
+#include "reduce.cuh"
+
+#include <cmath>
+#include <cstdlib>
+
+namespace smb {
+
+// device scalar block (doubles)
+// S_PAP..S_PAP+2: up to three partial p.Ap sums (interior / lower / upper boundary launches of the
+// distributed SpMV); contiguous so one all-reduce covers them.  Single GPU uses slot 0 only.
+enum { S_RR = 0, S_PAP = 1, S_RR_NEW = 4, S_THRESH = 5, S_ITER = 6, S_DONE = 7, S_COUNT = 8 };
+
+constexpr int kCgThreads = 256;
+
+// r = b - ap; p = r; S[RR_NEW] = r.r   (linearsolver.rs:38-40)
+template <class T>
+__global__ void __launch_bounds__(kCgThreads)
+cg_init_kernel(const T* __restrict__ b, const T* __restrict__ ap, T* __restrict__ r, T* __restrict__ p, uint64_t n,
+               double* __restrict__ S, double* __restrict__ partials, unsigned int* __restrict__ ticket) {
+    __shared__ double scratch[kCgThreads / 32 + 1];
+    using V = typename Vec16<T>::type;
+    constexpr int N = Vec16<T>::N;
+    const uint64_t tid = blockIdx.x * (uint64_t)kCgThreads + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * kCgThreads;
+    const uint64_t nvec = n / N;
+    T lane_acc[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) lane_acc[k] = T(0);
+    for (uint64_t i = tid; i < nvec; i += stride) {
+        Pack16<T> pb, pa;
+        pb.v = __ldg(reinterpret_cast<const V*>(b) + i);
+        pa.v = __ldg(reinterpret_cast<const V*>(ap) + i);
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            pb.e[k] = sub_rn(pb.e[k], pa.e[k]);
+            lane_acc[k] = add_rn(lane_acc[k], mul_rn(pb.e[k], pb.e[k]));
+        }
+        reinterpret_cast<V*>(r)[i] = pb.v;
+        reinterpret_cast<V*>(p)[i] = pb.v;
+    }
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < N; ++k) acc += (double)lane_acc[k];
+    for (uint64_t i = nvec * N + tid; i < n; i += stride) {
+        const T v = sub_rn(b[i], ap[i]);
+        r[i] = v; p[i] = v;
+        acc += (double)mul_rn(v, v);
+    }
+    const double bsum = block_sum<kCgThreads>(acc, scratch);
+    double total;
+    if (grid_sum<kCgThreads>(bsum, partials, ticket, scratch, total))
+        if (threadIdx.x == 0) S[S_RR_NEW] = (double)(T)total;
+}
+
+// B: x += (p * alpha); r -= (ap * alpha); S[RR_NEW] = r.r      (linearsolver.rs:45-51)
+template <class T>
+__global__ void __launch_bounds__(kCgThreads)
+cg_update_xr_kernel(T* __restrict__ x, T* __restrict__ r, const T* __restrict__ p, const T* __restrict__ ap, uint64_t n,
+                    double* __restrict__ S, double* __restrict__ partials, unsigned int* __restrict__ ticket) {
+    __shared__ double scratch[kCgThreads / 32 + 1];
+    if (__ldcg(S + S_DONE) != 0.0) return;
+    const T alpha = div_rn((T)__ldcg(S + S_RR), (T)(__ldcg(S + S_PAP) + __ldcg(S + S_PAP + 1) + __ldcg(S + S_PAP + 2)));
+    using V = typename Vec16<T>::type;
+    constexpr int N = Vec16<T>::N;
+    const uint64_t tid = blockIdx.x * (uint64_t)kCgThreads + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * kCgThreads;
+    const uint64_t nvec = n / N;
+    T lane_acc[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) lane_acc[k] = T(0);
+    for (uint64_t i = tid; i < nvec; i += stride) {
+        Pack16<T> px, pr, pp, pa;
+        pp.v = __ldg(reinterpret_cast<const V*>(p) + i);
+        pa.v = __ldg(reinterpret_cast<const V*>(ap) + i);
+        px.v = reinterpret_cast<V*>(x)[i];
+        pr.v = reinterpret_cast<V*>(r)[i];
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            px.e[k] = add_rn(px.e[k], mul_rn(pp.e[k], alpha));
+            pr.e[k] = sub_rn(pr.e[k], mul_rn(pa.e[k], alpha));
+            lane_acc[k] = add_rn(lane_acc[k], mul_rn(pr.e[k], pr.e[k]));
+        }
+        reinterpret_cast<V*>(x)[i] = px.v;
+        reinterpret_cast<V*>(r)[i] = pr.v;
+    }
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < N; ++k) acc += (double)lane_acc[k];
+    for (uint64_t i = nvec * N + tid; i < n; i += stride) {
+        x[i] = add_rn(x[i], mul_rn(p[i], alpha));
+        const T rv = sub_rn(r[i], mul_rn(ap[i], alpha));
+        r[i] = rv;
+        acc += (double)mul_rn(rv, rv);
+    }
+    const double bsum = block_sum<kCgThreads>(acc, scratch);
+    double total;
+    if (grid_sum<kCgThreads>(bsum, partials, ticket, scratch, total))
+        if (threadIdx.x == 0) S[S_RR_NEW] = (double)(T)total;
+}
+
+// C: stop test, bookkeeping, p = (p * beta) + r                  (linearsolver.rs:52-59)
+template <class T>
+__global__ void __launch_bounds__(kCgThreads)
+cg_update_p_kernel(T* __restrict__ p, const T* __restrict__ r, uint64_t n, double* __restrict__ S,
+                   double* __restrict__ history, uint64_t hist_cap) {
+    if (__ldcg(S + S_DONE) != 0.0) return;
+    const double rr_new = __ldcg(S + S_RR_NEW);
+    const double res = sqrt(rr_new);                       // f64::sqrt(r_norm_squared.into())
+    const bool done = res < __ldcg(S + S_THRESH);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const uint64_t it = (uint64_t)S[S_ITER];
+        if (history && it < hist_cap) history[it] = res;
+        S[S_ITER] = (double)(it + 1);
+        if (done) S[S_DONE] = 1.0;
+    }
+    if (done) return;
+    const T beta = div_rn((T)rr_new, (T)__ldcg(S + S_RR));
+    using V = typename Vec16<T>::type;
+    constexpr int N = Vec16<T>::N;
+    const uint64_t tid = blockIdx.x * (uint64_t)kCgThreads + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * kCgThreads;
+    const uint64_t nvec = n / N;
+    for (uint64_t i = tid; i < nvec; i += stride) {
+        Pack16<T> pp, pr;
+        pp.v = reinterpret_cast<V*>(p)[i];
+        pr.v = __ldg(reinterpret_cast<const V*>(r) + i);
+#pragma unroll
+        for (int k = 0; k < N; ++k) pp.e[k] = add_rn(mul_rn(pp.e[k], beta), pr.e[k]);
+        reinterpret_cast<V*>(p)[i] = pp.v;
+    }
+    for (uint64_t i = nvec * N + tid; i < n; i += stride) p[i] = add_rn(mul_rn(p[i], beta), r[i]);
+}
+
+void cg_free(CgWork& w) {
+    if (w.r) cudaFree(w.r);
+    if (w.p) cudaFree(w.p);
+    if (w.ap) cudaFree(w.ap);
+    if (w.scalars) cudaFree(w.scalars);
+    if (w.scalars_host) cudaFreeHost(w.scalars_host);
+    if (w.history) cudaFree(w.history);
+    if (w.graph) cudaGraphExecDestroy(w.graph);
+    w = CgWork();
+}
+
+static unsigned cg_grid(const smb200_ctx* ctx, uint64_t n, int vt) {
+    const uint64_t items = n / (16 / vsize(vt)) + 1;
+    uint64_t need = (items + kCgThreads - 1) / kCgThreads;
+    const uint64_t cap = (uint64_t)ctx->sm_count * 8;
+    return (unsigned)(need < cap ? need : cap);
+}
+
+// p_cap: allocated elements of p (dist solves keep ghost room behind the owned part)
+smb200_status cg_prepare(smb200_ctx* ctx, CgWork& w, int vt, uint64_t n, uint64_t p_cap, uint64_t iter_max) {
+    if (w.n != n || !w.r || w.hist_cap < (iter_max < (1u << 20) ? iter_max : (1u << 20))) {
+        cudaStreamSynchronize(ctx->stream);
+        cg_free(w);
+        const size_t es = vsize(vt);
+        SMB_TRY(dev_alloc(&w.r, n * es));
+        SMB_TRY(dev_alloc(&w.p, (p_cap > n ? p_cap : n) * es));
+        SMB_TRY(dev_alloc(&w.ap, n * es));
+        SMB_CUDA(cudaMemsetAsync(w.p, 0, (p_cap > n ? p_cap : n) * es + kPadBytes, ctx->stream));
+        SMB_CUDA(cudaMalloc(&w.scalars, S_COUNT * sizeof(double)));
+        SMB_CUDA(cudaHostAlloc(&w.scalars_host, 4 * S_COUNT * sizeof(double), cudaHostAllocDefault));
+        w.hist_cap = iter_max < (1u << 20) ? iter_max : (1u << 20);
+        if (w.hist_cap == 0) w.hist_cap = 1;
+        SMB_CUDA(cudaMalloc(&w.history, w.hist_cap * sizeof(double)));
+        w.n = n;
+    }
+    SMB_TRY(ensure_reduction_scratch(ctx, (size_t)ctx->sm_count * 8 + 16));
+    return SMB200_OK;
+}
+
+smb200_status cg_init_launch(smb200_ctx* ctx, CgWork& w, int vt, const void* b, uint64_t n) {
+    const unsigned g = cg_grid(ctx, n, vt);
+    if (vt == SMB200_F64) cg_init_kernel<double><<<g, kCgThreads, 0, ctx->stream>>>((const double*)b, (const double*)w.ap, (double*)w.r, (double*)w.p, n, w.scalars, ctx->red_partials, ctx->red_ticket);
+    else cg_init_kernel<float><<<g, kCgThreads, 0, ctx->stream>>>((const float*)b, (const float*)w.ap, (float*)w.r, (float*)w.p, n, w.scalars, ctx->red_partials, ctx->red_ticket);
+    count_launch();
+    SMB_CUDA(cudaGetLastError());
+    return SMB200_OK;
+}
+
+smb200_status cg_xr_launch(smb200_ctx* ctx, CgWork& w, int vt, void* x, uint64_t n) {
+    const unsigned g = cg_grid(ctx, n, vt);
+    if (vt == SMB200_F64) cg_update_xr_kernel<double><<<g, kCgThreads, 0, ctx->stream>>>((double*)x, (double*)w.r, (const double*)w.p, (const double*)w.ap, n, w.scalars, ctx->red_partials, ctx->red_ticket);
+    else cg_update_xr_kernel<float><<<g, kCgThreads, 0, ctx->stream>>>((float*)x, (float*)w.r, (const float*)w.p, (const float*)w.ap, n, w.scalars, ctx->red_partials, ctx->red_ticket);
+    count_launch();
+    SMB_CUDA(cudaGetLastError());
+    return SMB200_OK;
+}
+
+smb200_status cg_p_launch(smb200_ctx* ctx, CgWork& w, int vt, uint64_t n) {
+    const unsigned g = cg_grid(ctx, n, vt);
+    if (vt == SMB200_F64) cg_update_p_kernel<double><<<g, kCgThreads, 0, ctx->stream>>>((double*)w.p, (const double*)w.r, n, w.scalars, w.history, w.hist_cap);
+    else cg_update_p_kernel<float><<<g, kCgThreads, 0, ctx->stream>>>((float*)w.p, (const float*)w.r, n, w.scalars, w.history, w.hist_cap);
+    count_launch();
+    SMB_CUDA(cudaGetLastError());
+    return SMB200_OK;
+}
+
+// One CG iteration on the context stream (single GPU).
+static smb200_status cg_iteration(smb200_crs* a, void* x) {
+    smb200_ctx* ctx = a->ctx;
+    CgWork& w = a->cg;
+    SMB_TRY(spmv_launch_cg(a, a->plan, 0, a->n_rows, w.p, w.ap, w.p, w.scalars, 0, true));
+    SMB_TRY(cg_xr_launch(ctx, w, a->vt, x, a->n_rows));
+    SMB_TRY(cg_p_launch(ctx, w, a->vt, a->n_rows));
+    return SMB200_OK;
+}
+
+}  // namespace smb
+
+using namespace smb;
+
+extern "C" {
+
+smb200_status smb200_cg_solve(smb200_crs* a, const smb200_vec* b, smb200_vec* x, double tol, int32_t relative,
+                              uint64_t iter_max, smb200_cg_stats* stats) {
+    SMB_REQUIRE(a && b && x, SMB200_ERR_INVALID, "cg_solve: NULL argument");
+    SMB_REQUIRE(b->vt == a->vt && x->vt == a->vt, SMB200_ERR_INVALID, "cg_solve: value types differ");
+    SMB_REQUIRE(b->ctx == a->ctx && x->ctx == a->ctx, SMB200_ERR_INVALID, "cg_solve: operands belong to different contexts");
+    SMB_REQUIRE(a->n_rows == a->n_cols, SMB200_ERR_NOT_SQUARE, "Matrix is not symmetric");            // linearsolver.rs:30-32
+    SMB_REQUIRE(a->n_rows == b->n && a->n_rows == x->n, SMB200_ERR_SIZE_MISMATCH, "Matrix and vector size mismatch");  // :33-36
+    smb200_ctx* ctx = a->ctx;
+    CgWork& w = a->cg;
+    const uint64_t n = a->n_rows;
+    const uint64_t launches0 = g_launches;
+    if (stats) memset(stats, 0, sizeof *stats);
+    if (n == 0) return SMB200_OK;
+    SMB_CUDA(cudaSetDevice(ctx->device));
+    if (!a->plan.built) SMB_TRY(plan_build(a));
+    SMB_TRY(cg_prepare(ctx, w, a->vt, n, n, iter_max));
+
+    double threshold = tol;
+    if (relative) {
+        double bb = 0.0;
+        SMB_TRY(dot_launch(ctx, a->vt, b->d, b->d, n, 0));
+        SMB_TRY(fetch_result(ctx, 0, &bb));
+        threshold = tol * sqrt(bb);
+    }
+    cudaEvent_t ev0, ev1;
+    SMB_CUDA(cudaEventCreate(&ev0));
+    SMB_CUDA(cudaEventCreate(&ev1));
+    SMB_CUDA(cudaEventRecord(ev0, ctx->stream));
+
+    double init[S_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0};
+    init[S_THRESH] = threshold;
+    memcpy(w.scalars_host + 3 * S_COUNT, init, sizeof init);
+    SMB_CUDA(cudaMemcpyAsync(w.scalars, w.scalars_host + 3 * S_COUNT, sizeof init, cudaMemcpyHostToDevice, ctx->stream));
+    // r = b - A x ; p = r ; rr = r.r
+    SMB_TRY(spmv_launch_plan(a, a->plan, 0, n, x->d, w.ap, nullptr, 0));
+    SMB_TRY(cg_init_launch(ctx, w, a->vt, b->d, n));
+
+    const char* genv = getenv("SMB200_CG_GRAPH");
+    const bool use_graph = !(genv && genv[0] == '0');
+    const char* benv = getenv("SMB200_CG_BATCH");
+    int batch = benv ? atoi(benv) : 8;
+    if (batch < 1) batch = 1;
+
+    uint64_t launched = 0;
+    cudaEvent_t poll_ev[2];
+    SMB_CUDA(cudaEventCreateWithFlags(&poll_ev[0], cudaEventDisableTiming));
+    SMB_CUDA(cudaEventCreateWithFlags(&poll_ev[1], cudaEventDisableTiming));
+    smb200_status st = SMB200_OK;
+    uint64_t rounds = 0;
+    bool finished = false;
+    // first iteration eagerly: performs every lazy initialisation outside of stream capture
+    if (iter_max > 0) { st = cg_iteration(a, x->d); launched = 1; }
+    while (st == SMB200_OK && !finished) {
+        // publish (iteration, done) of everything launched so far
+        const int slot = (int)(rounds & 1);
+        cudaError_t e = cudaMemcpyAsync(w.scalars_host + slot * S_COUNT, w.scalars, S_COUNT * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaEventRecord(poll_ev[slot], ctx->stream);
+        if (e != cudaSuccess) { set_error("cg_solve: %s", cudaGetErrorString(e)); st = SMB200_ERR_CUDA; break; }
+        // enqueue the next batch before looking at the previous snapshot
+        uint64_t nb = iter_max - launched < (uint64_t)batch ? iter_max - launched : (uint64_t)batch;
+        if (nb > 0) {
+            if (use_graph && nb == (uint64_t)batch) {
+                if (!w.graph || w.graph_batch != batch || w.graph_x != x->d || w.graph_partials != ctx->red_partials ||
+                    w.graph_plan != a->plan.blk_rows) {
+                    if (w.graph) { cudaGraphExecDestroy(w.graph); w.graph = nullptr; }
+                    cudaGraph_t graph = nullptr;
+                    e = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal);
+                    if (e == cudaSuccess) {
+                        for (int k = 0; k < batch && st == SMB200_OK; ++k) st = cg_iteration(a, x->d);
+                        cudaError_t e2 = cudaStreamEndCapture(ctx->stream, &graph);
+                        if (st == SMB200_OK && e2 != cudaSuccess) e = e2;
+                    }
+                    if (st == SMB200_OK && e == cudaSuccess) e = cudaGraphInstantiate(&w.graph, graph, 0);
+                    if (graph) cudaGraphDestroy(graph);
+                    if (e != cudaSuccess && st == SMB200_OK) { set_error("cg_solve: graph capture failed: %s", cudaGetErrorString(e)); st = SMB200_ERR_CUDA; }
+                    if (st != SMB200_OK) break;
+                    w.graph_batch = batch;
+                    w.graph_x = x->d;
+                    w.graph_partials = ctx->red_partials;
+                    w.graph_plan = a->plan.blk_rows;
+                }
+                e = cudaGraphLaunch(w.graph, ctx->stream);
+                if (e != cudaSuccess) { set_error("cg_solve: graph launch failed: %s", cudaGetErrorString(e)); st = SMB200_ERR_CUDA; break; }
+                count_launch(3 * (uint64_t)batch);
+            } else {
+                for (uint64_t k = 0; k < nb && st == SMB200_OK; ++k) st = cg_iteration(a, x->d);
+                if (st != SMB200_OK) break;
+            }
+            launched += nb;
+        }
+        // look at the snapshot taken before this batch
+        e = cudaEventSynchronize(poll_ev[slot]);
+        if (e != cudaSuccess) { set_error("cg_solve: %s", cudaGetErrorString(e)); st = SMB200_ERR_CUDA; break; }
+        const double* snap = w.scalars_host + slot * S_COUNT;
+        if (snap[S_DONE] != 0.0) finished = true;
+        if (nb == 0) finished = true;
+        ++rounds;
+    }
+    if (st == SMB200_OK) {
+        cudaError_t e = cudaEventRecord(ev1, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(w.scalars_host, w.scalars, S_COUNT * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { set_error("cg_solve: %s", cudaGetErrorString(e)); st = SMB200_ERR_CUDA; }
+    }
+    if (st == SMB200_OK) {
+        const double* S = w.scalars_host;
+        const uint64_t iters = (uint64_t)S[S_ITER];
+        w.history_host.assign(iters < w.hist_cap ? iters : w.hist_cap, 0.0);
+        if (!w.history_host.empty())
+            cudaMemcpy(w.history_host.data(), w.history, w.history_host.size() * sizeof(double), cudaMemcpyDeviceToHost);
+        if (stats) {
+            stats->iterations = iters;
+            stats->final_residual = sqrt(S[S_RR_NEW]);
+            stats->converged = S[S_DONE] != 0.0;
+            cudaEventElapsedTime(&stats->device_ms, ev0, ev1);
+            stats->launches = g_launches - launches0;
+        }
+    } else {
+        cudaStreamSynchronize(ctx->stream);
+    }
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+    cudaEventDestroy(poll_ev[0]); cudaEventDestroy(poll_ev[1]);
+    return st;
+}
+
+smb200_status smb200_cg_history(const smb200_crs* a, double* out, uint64_t cap, uint64_t* n) {
+    SMB_REQUIRE(a && n, SMB200_ERR_INVALID, "cg_history: NULL argument");
+    const auto& h = a->cg.history_host;
+    *n = h.size();
+    if (out) for (uint64_t k = 0; k < cap && k < h.size(); ++k) out[k] = h[k];
+    return SMB200_OK;
+}
+
+}  // extern "C"

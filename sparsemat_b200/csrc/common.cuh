@@ -1,0 +1,182 @@
+// libsmb200 internals shared by all translation units.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/smb200.h"
+
+namespace smb {
+
+// ---- error plumbing: the C layer never throws or aborts ------------------------------------------
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+#define SMB_FAIL(code, ...)            \
+    do {                               \
+        ::smb::set_error(__VA_ARGS__); \
+        return (code);                 \
+    } while (0)
+
+#define SMB_CUDA(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t e__ = (expr);                                                                   \
+        if (e__ != cudaSuccess) {                                                                   \
+            ::smb::set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(e__), __FILE__, __LINE__, \
+                             cudaGetErrorString(e__));                                              \
+            return e__ == cudaErrorMemoryAllocation ? SMB200_ERR_OOM : SMB200_ERR_CUDA;             \
+        }                                                                                           \
+    } while (0)
+
+#define SMB_TRY(expr)                      \
+    do {                                   \
+        smb200_status s__ = (expr);        \
+        if (s__ != SMB200_OK) return s__;  \
+    } while (0)
+
+#define SMB_REQUIRE(cond, code, ...)            \
+    do {                                        \
+        if (!(cond)) SMB_FAIL(code, __VA_ARGS__); \
+    } while (0)
+
+// kernels launched by this library (bench evidence: gpu_launches)
+extern thread_local uint64_t g_launches;
+inline void count_launch(uint64_t n = 1) { g_launches += n; }
+
+inline size_t vsize(int vt) { return vt == SMB200_F64 ? 8 : 4; }
+inline size_t isize(int it) { return it == SMB200_U64 ? 8 : 4; }
+
+// All device arrays are padded so that 128-bit loads and 16-byte bulk copies that start at an
+// aligned-down address and end at an aligned-up one never leave the allocation.
+constexpr size_t kPadBytes = 256;
+
+}  // namespace smb
+
+struct smb200_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    cudaStream_t aux_stream = nullptr;   // halo traffic / overlap
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    int sm_count = 0;
+    size_t l2_bytes = 0, l2_persist_max = 0;
+    // scratch for reductions: partial sums + ticket + result slots
+    double* red_partials = nullptr;      // [red_cap]
+    size_t red_cap = 0;
+    unsigned int* red_ticket = nullptr;  // zero between uses
+    double* red_result = nullptr;        // device [8]
+    double* red_result_host = nullptr;   // pinned [8]
+    void* flush_buf = nullptr;
+    size_t flush_bytes = 0;
+    // staging for *_host calls
+    void* stage_x = nullptr; size_t stage_x_bytes = 0;
+    void* stage_y = nullptr; size_t stage_y_bytes = 0;
+    // NCCL (dist.cu); opaque here
+    void* comm = nullptr;
+    int rank = 0, world = 1;
+};
+
+struct smb200_vec {
+    smb200_ctx* ctx = nullptr;
+    int vt = SMB200_F32;
+    uint64_t n = 0;        // dim()
+    uint64_t cap = 0;      // allocated elements (>= n; dist vectors keep ghost room behind n)
+    void* d = nullptr;
+    bool owned = true;
+};
+
+struct smb200_event {
+    smb200_ctx* ctx = nullptr;
+    cudaEvent_t ev = nullptr;
+};
+
+namespace smb {
+
+// ---- SpMV plan: built once per matrix (and per variant) -------------------------------------------
+struct SpmvPlan {
+    int variant = SMB200_SPMV_AUTO;     // resolved
+    int lanes = 0;
+    uint32_t flags = 0;
+    uint64_t n_blocks = 0;              // STREAM*: CTAs
+    void* blk_rows = nullptr;           // STREAM*: [n_blocks+1] row split points, index type
+    void* blk_win = nullptr;            // BANDED: [2*n_blocks] (cmin, cmax+1) per block, index type
+    uint64_t max_win = 0;               // BANDED: widest window (elements)
+    bool built = false;
+};
+
+// CG workspace kept with the matrix so repeated solves do not reallocate.
+struct CgWork {
+    uint64_t n = 0;
+    void* r = nullptr; void* p = nullptr; void* ap = nullptr;
+    double* scalars = nullptr;          // device: see cg.cu
+    double* scalars_host = nullptr;     // pinned mirror
+    double* history = nullptr;          // device [hist_cap]
+    uint64_t hist_cap = 0;
+    std::vector<double> history_host;
+    cudaGraphExec_t graph = nullptr;    // batch of iterations
+    int graph_batch = 0;
+    const void* graph_x = nullptr;      // pointers the graph was captured with
+    const void* graph_partials = nullptr;
+    const void* graph_plan = nullptr;
+};
+
+}  // namespace smb
+
+struct smb200_crs {
+    smb200_ctx* ctx = nullptr;
+    int vt = SMB200_F32, it = SMB200_U32;
+    uint64_t n_rows = 0, n_cols = 0, nnz = 0;
+    void* values = nullptr;
+    void* columns = nullptr;
+    void* offsets = nullptr;            // [n_rows+1] (nullptr for the 0x0 matrix)
+    uint64_t max_row_len = 0;
+    int want_variant = SMB200_SPMV_AUTO;
+    int want_lanes = 0;
+    uint32_t want_flags = 0;
+    smb::SpmvPlan plan;
+    smb::CgWork cg;
+    uint64_t x_extra = 0;               // dist: number of ghost entries appended to x (n_cols counts them)
+};
+
+namespace smb {
+
+// implemented across the .cu files
+smb200_status dev_alloc(void** p, size_t bytes);
+smb200_status crs_alloc(smb200_ctx* ctx, int vt, int it, uint64_t n_rows, uint64_t n_cols, uint64_t nnz,
+                        smb200_crs** out);
+smb200_status crs_finalize(smb200_crs* m, bool validate);   // row stats (+ validation), invalidates plan
+smb200_status exclusive_scan_inplace(smb200_ctx* ctx, int it, void* data, uint64_t n, uint64_t* total);
+smb200_status plan_build(smb200_crs* m);
+smb200_status plan_build_range(smb200_crs* m, SpmvPlan& p, int want_variant, int want_lanes, uint32_t flags,
+                               uint64_t row_begin, uint64_t row_end);
+void plan_free(SpmvPlan& p);
+void cg_free(CgWork& w);
+smb200_status spmv_launch_plan(smb200_crs* m, const SpmvPlan& p, uint64_t row_begin, uint64_t row_end, const void* x,
+                               void* y, const void* w, int dot_slot);
+smb200_status spmv_launch_cg(smb200_crs* m, const SpmvPlan& p, uint64_t row_begin, uint64_t row_end, const void* x,
+                             void* y, const void* w, double* S, int slot, bool roll);
+smb200_status vec_create_cap(smb200_ctx* ctx, int vt, uint64_t n, uint64_t cap, smb200_vec** out);
+smb200_status gen_laplace_block(smb200_ctx* ctx, int vt, int it, uint64_t nx, uint64_t ny, uint64_t nz, uint64_t row_lo,
+                                uint64_t row_hi, int local_cols, uint64_t n_lo_ghost, uint64_t n_cols_out,
+                                smb200_crs** out);
+smb200_status cg_prepare(smb200_ctx* ctx, CgWork& w, int vt, uint64_t n, uint64_t p_cap, uint64_t iter_max);
+smb200_status cg_init_launch(smb200_ctx* ctx, CgWork& w, int vt, const void* b, uint64_t n);
+smb200_status cg_xr_launch(smb200_ctx* ctx, CgWork& w, int vt, void* x, uint64_t n);
+smb200_status cg_p_launch(smb200_ctx* ctx, CgWork& w, int vt, uint64_t n);
+
+// y = A x on m->ctx->stream.  If dot_out != nullptr, also accumulates sum_r w[r]*y[r] into the
+// reduction scratch and leaves the result in ctx->red_result[slot] (fused SpMV + dot, K7a).
+smb200_status spmv_launch(smb200_crs* m, const void* x, void* y, const void* w, int dot_slot,
+                          uint64_t row_begin = 0, uint64_t row_end = UINT64_MAX);
+
+// reductions leave their value (as double, already rounded to T) in ctx->red_result[slot]
+smb200_status dot_launch(smb200_ctx* ctx, int vt, const void* x, const void* y, uint64_t n, int slot);
+smb200_status fetch_result(smb200_ctx* ctx, int slot, double* out);   // D2H + sync
+smb200_status ensure_reduction_scratch(smb200_ctx* ctx, size_t n_partials);
+
+}  // namespace smb

@@ -1,0 +1,514 @@
+// K9 — one process per GPU: row-block distributed SpMV and CG.
+//
+// Partitioning is SparseMatPar's model (sparsemat_par.rs:20-35): contiguous row blocks, every block
+// needs the slice of x its columns touch.  The reference's sketch replicates x (`Arc<rhs>`,
+// sparsemat_par.rs:39-67); here each rank keeps only [owned | ghosts] and the ghosts are refreshed by a
+// neighbour exchange (NCCL send/recv over NVLink/NVSwitch) on a side stream while the interior rows
+// — those that reference no ghost — are already being multiplied on the main stream.  The two CG dot
+// products are all-reduced as 3+1 doubles per iteration.
+//
+// NCCL is loaded with dlopen at smb200_comm_init time, so single-GPU users carry no NCCL dependency
+// and the library loads on machines without it.
+#include "common.cuh"
+
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+
+namespace smb {
+
+// ---- minimal NCCL surface (ABI-stable since 2.x) ---------------------------------------------------------
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+enum { kNcclUint8 = 1, kNcclUint64 = 5, kNcclFloat32 = 7, kNcclFloat64 = 8 };
+enum { kNcclSum = 0 };
+
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+static NcclApi g_nccl;
+
+static smb200_status nccl_load() {
+    if (g_nccl.lib) return SMB200_OK;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    void* lib = nullptr;
+    for (const char* n : names) {
+        lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (lib) break;
+    }
+    SMB_REQUIRE(lib, SMB200_ERR_NCCL, "NCCL not found (dlopen libnccl.so.2): %s", dlerror());
+#define LOAD(field, sym)                                                                 \
+    do {                                                                                 \
+        *(void**)(&g_nccl.field) = dlsym(lib, sym);                                      \
+        if (!g_nccl.field) { dlclose(lib); SMB_FAIL(SMB200_ERR_NCCL, "NCCL symbol %s missing", sym); } \
+    } while (0)
+    LOAD(GetUniqueId, "ncclGetUniqueId");
+    LOAD(CommInitRank, "ncclCommInitRank");
+    LOAD(CommDestroy, "ncclCommDestroy");
+    LOAD(AllReduce, "ncclAllReduce");
+    LOAD(AllGather, "ncclAllGather");
+    LOAD(Send, "ncclSend");
+    LOAD(Recv, "ncclRecv");
+    LOAD(GroupStart, "ncclGroupStart");
+    LOAD(GroupEnd, "ncclGroupEnd");
+    LOAD(GetErrorString, "ncclGetErrorString");
+#undef LOAD
+    g_nccl.lib = lib;
+    return SMB200_OK;
+}
+
+#define SMB_NCCL(expr)                                                                                   \
+    do {                                                                                                 \
+        ncclResult_t r__ = (expr);                                                                       \
+        if (r__ != 0) SMB_FAIL(SMB200_ERR_NCCL, "NCCL error at %s:%d: %s", __FILE__, __LINE__, g_nccl.GetErrorString(r__)); \
+    } while (0)
+
+static int nccl_vtype(int vt) { return vt == SMB200_F64 ? kNcclFloat64 : kNcclFloat32; }
+
+template <class T>
+__global__ void pack_kernel(const T* __restrict__ x, const uint64_t* __restrict__ idx, uint64_t n, T* __restrict__ out) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; k < n; k += stride) out[k] = x[idx[k]];
+}
+
+}  // namespace smb
+
+struct smb200_dist {
+    smb200_ctx* ctx = nullptr;
+    int vt = SMB200_F32, it = SMB200_U32;
+    uint64_t n_global = 0, row_lo = 0, n_local = 0, n_ghost = 0;
+    std::vector<uint64_t> bounds;
+    smb200_crs* local = nullptr;                 // columns in local numbering [owned | ghosts]
+    // receive side: ghosts are sorted by global id, hence grouped by owner
+    std::vector<uint64_t> recv_count, recv_off;  // per peer, in elements, offset into the ghost region
+    // send side
+    std::vector<uint64_t> send_count, send_off;  // per peer, offset into send_idx / send_buf
+    std::vector<int> send_contig;                // 1: the peer wants a contiguous run starting at send_first
+    std::vector<uint64_t> send_first;
+    uint64_t* send_idx = nullptr;                // device: local row ids to pack, grouped by peer
+    void* send_buf = nullptr;                    // device: packed values
+    uint64_t total_send = 0;
+    // rows [int_begin, int_end) reference no ghost: multiplied while the exchange is in flight
+    uint64_t int_begin = 0, int_end = 0;
+    smb::SpmvPlan plan_int, plan_lo, plan_hi;
+};
+
+namespace smb {
+
+static smb200_status dist_build_plans(smb200_dist* d) {
+    smb200_crs* m = d->local;
+    SMB_TRY(plan_build_range(m, d->plan_int, m->want_variant, m->want_lanes, m->want_flags, d->int_begin, d->int_end));
+    SMB_TRY(plan_build_range(m, d->plan_lo, m->want_variant, m->want_lanes, m->want_flags, 0, d->int_begin));
+    SMB_TRY(plan_build_range(m, d->plan_hi, m->want_variant, m->want_lanes, m->want_flags, d->int_end, d->n_local));
+    return SMB200_OK;
+}
+
+// Refresh the ghost entries of x: pack on the main stream, send/recv on the side stream.
+// On return the side stream has recorded ctx->ev_b when the ghosts are in place.
+static smb200_status dist_exchange_begin(smb200_dist* d, void* x) {
+    smb200_ctx* ctx = d->ctx;
+    const int world = ctx->world, me = ctx->rank;
+    if (world == 1 || (d->n_ghost == 0 && d->total_send == 0)) return SMB200_OK;
+    const size_t es = vsize(d->vt);
+    for (int q = 0; q < world; ++q) {
+        if (q == me || d->send_count[q] == 0 || d->send_contig[q]) continue;
+        const unsigned g = (unsigned)std::min<uint64_t>((d->send_count[q] + 255) / 256, (uint64_t)ctx->sm_count * 4);
+        if (d->vt == SMB200_F64) pack_kernel<double><<<g, 256, 0, ctx->stream>>>((const double*)x, d->send_idx + d->send_off[q], d->send_count[q], (double*)d->send_buf + d->send_off[q]);
+        else pack_kernel<float><<<g, 256, 0, ctx->stream>>>((const float*)x, d->send_idx + d->send_off[q], d->send_count[q], (float*)d->send_buf + d->send_off[q]);
+        count_launch();
+    }
+    SMB_CUDA(cudaEventRecord(ctx->ev_a, ctx->stream));
+    SMB_CUDA(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_a, 0));
+    ncclComm_t comm = (ncclComm_t)ctx->comm;
+    SMB_NCCL(g_nccl.GroupStart());
+    for (int q = 0; q < world; ++q) {
+        if (q == me) continue;
+        if (d->send_count[q]) {
+            const char* src = d->send_contig[q] ? (const char*)x + d->send_first[q] * es : (const char*)d->send_buf + d->send_off[q] * es;
+            SMB_NCCL(g_nccl.Send(src, d->send_count[q], nccl_vtype(d->vt), q, comm, ctx->aux_stream));
+        }
+        if (d->recv_count[q]) {
+            char* dst = (char*)x + (d->n_local + d->recv_off[q]) * es;
+            SMB_NCCL(g_nccl.Recv(dst, d->recv_count[q], nccl_vtype(d->vt), q, comm, ctx->aux_stream));
+        }
+    }
+    SMB_NCCL(g_nccl.GroupEnd());
+    SMB_CUDA(cudaEventRecord(ctx->ev_b, ctx->aux_stream));
+    return SMB200_OK;
+}
+
+static smb200_status dist_exchange_end(smb200_dist* d) {
+    smb200_ctx* ctx = d->ctx;
+    if (ctx->world == 1 || (d->n_ghost == 0 && d->total_send == 0)) return SMB200_OK;
+    SMB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_b, 0));
+    return SMB200_OK;
+}
+
+// y = (A x)_local.  S == nullptr: plain product.  S != nullptr: CG kernel A with p.Ap partials in S.
+static smb200_status dist_spmv_impl(smb200_dist* d, void* x, void* y, double* S) {
+    smb200_crs* m = d->local;
+    SMB_TRY(dist_exchange_begin(d, x));
+    if (S) SMB_TRY(spmv_launch_cg(m, d->plan_int, d->int_begin, d->int_end, x, y, x, S, 0, true));
+    else SMB_TRY(spmv_launch_plan(m, d->plan_int, d->int_begin, d->int_end, x, y, nullptr, 0));
+    SMB_TRY(dist_exchange_end(d));
+    if (S) {
+        SMB_TRY(spmv_launch_cg(m, d->plan_lo, 0, d->int_begin, x, y, x, S, 1, d->int_end == d->int_begin));
+        SMB_TRY(spmv_launch_cg(m, d->plan_hi, d->int_end, d->n_local, x, y, x, S, 2, d->int_end == d->int_begin && d->int_begin == 0));
+    } else {
+        SMB_TRY(spmv_launch_plan(m, d->plan_lo, 0, d->int_begin, x, y, nullptr, 0));
+        SMB_TRY(spmv_launch_plan(m, d->plan_hi, d->int_end, d->n_local, x, y, nullptr, 0));
+    }
+    return SMB200_OK;
+}
+
+// Exchange "who needs what": recv_count is known locally; learn send lists from the peers.
+static smb200_status dist_setup_exchange(smb200_dist* d, const std::vector<uint64_t>& ghosts) {
+    smb200_ctx* ctx = d->ctx;
+    const int world = ctx->world, me = ctx->rank;
+    d->recv_off.assign(world, 0);
+    d->send_count.assign(world, 0);
+    d->send_off.assign(world, 0);
+    d->send_contig.assign(world, 0);
+    d->send_first.assign(world, 0);
+    uint64_t run = 0;
+    for (int q = 0; q < world; ++q) { d->recv_off[q] = run; run += d->recv_count[q]; }
+    if (world == 1) return SMB200_OK;
+    ncclComm_t comm = (ncclComm_t)ctx->comm;
+    // all-gather the world x world matrix of counts
+    uint64_t* d_counts = nullptr;
+    SMB_CUDA(cudaMalloc(&d_counts, (size_t)world * world * sizeof(uint64_t)));
+    SMB_CUDA(cudaMemcpyAsync(d_counts + (size_t)me * world, d->recv_count.data(), world * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    SMB_NCCL(g_nccl.AllGather(d_counts + (size_t)me * world, d_counts, world, kNcclUint64, comm, ctx->stream));
+    std::vector<uint64_t> counts((size_t)world * world);
+    SMB_CUDA(cudaMemcpyAsync(counts.data(), d_counts, counts.size() * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    SMB_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_counts);
+    run = 0;
+    for (int q = 0; q < world; ++q) {
+        d->send_count[q] = (q == me) ? 0 : counts[(size_t)q * world + me];   // what q receives from me
+        d->send_off[q] = run;
+        run += d->send_count[q];
+    }
+    d->total_send = run;
+    // ship the ghost id lists to their owners
+    uint64_t *d_ghosts = nullptr, *d_want = nullptr;
+    SMB_CUDA(cudaMalloc(&d_ghosts, (ghosts.size() + 1) * sizeof(uint64_t)));
+    SMB_CUDA(cudaMalloc(&d_want, (d->total_send + 1) * sizeof(uint64_t)));
+    if (!ghosts.empty()) SMB_CUDA(cudaMemcpyAsync(d_ghosts, ghosts.data(), ghosts.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    SMB_NCCL(g_nccl.GroupStart());
+    for (int q = 0; q < world; ++q) {
+        if (q == me) continue;
+        if (d->recv_count[q]) SMB_NCCL(g_nccl.Send(d_ghosts + d->recv_off[q], d->recv_count[q], kNcclUint64, q, comm, ctx->stream));
+        if (d->send_count[q]) SMB_NCCL(g_nccl.Recv(d_want + d->send_off[q], d->send_count[q], kNcclUint64, q, comm, ctx->stream));
+    }
+    SMB_NCCL(g_nccl.GroupEnd());
+    std::vector<uint64_t> want(d->total_send);
+    if (d->total_send) SMB_CUDA(cudaMemcpyAsync(want.data(), d_want, d->total_send * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    SMB_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_ghosts);
+    for (uint64_t k = 0; k < d->total_send; ++k) {
+        if (want[k] < d->row_lo || want[k] >= d->row_lo + d->n_local) {
+            cudaFree(d_want);
+            SMB_FAIL(SMB200_ERR_INVALID, "dist: a peer asked for row %llu which this rank does not own", (unsigned long long)want[k]);
+        }
+        want[k] -= d->row_lo;
+    }
+    for (int q = 0; q < world; ++q) {
+        const uint64_t c = d->send_count[q], o = d->send_off[q];
+        bool contig = c > 0;
+        for (uint64_t k = 1; k < c && contig; ++k) contig = want[o + k] == want[o + k - 1] + 1;
+        d->send_contig[q] = contig ? 1 : 0;
+        d->send_first[q] = c ? want[o] : 0;
+    }
+    d->send_idx = d_want;
+    if (d->total_send) SMB_CUDA(cudaMemcpyAsync(d->send_idx, want.data(), d->total_send * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    SMB_TRY(dev_alloc(&d->send_buf, (d->total_send + 1) * vsize(d->vt)));
+    SMB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SMB200_OK;
+}
+
+}  // namespace smb
+
+using namespace smb;
+
+extern "C" {
+
+smb200_status smb200_comm_unique_id(void* out128) {
+    SMB_REQUIRE(out128, SMB200_ERR_INVALID, "comm_unique_id: NULL argument");
+    SMB_TRY(nccl_load());
+    ncclUniqueId id;
+    SMB_NCCL(g_nccl.GetUniqueId(&id));
+    memcpy(out128, &id, sizeof id);
+    return SMB200_OK;
+}
+
+smb200_status smb200_comm_init(smb200_ctx* ctx, int32_t rank, int32_t world, const void* uid128) {
+    SMB_REQUIRE(ctx && (uid128 || world == 1), SMB200_ERR_INVALID, "comm_init: NULL argument");
+    SMB_REQUIRE(world >= 1 && rank >= 0 && rank < world, SMB200_ERR_INVALID, "comm_init: bad rank %d / world %d", rank, world);
+    SMB_REQUIRE(!ctx->comm, SMB200_ERR_INVALID, "comm_init: communicator already initialised");
+    ctx->rank = rank;
+    ctx->world = world;
+    if (world == 1) return SMB200_OK;
+    SMB_TRY(nccl_load());
+    SMB_CUDA(cudaSetDevice(ctx->device));
+    ncclUniqueId id;
+    memcpy(&id, uid128, sizeof id);
+    ncclComm_t comm = nullptr;
+    SMB_NCCL(g_nccl.CommInitRank(&comm, world, id, rank));
+    ctx->comm = comm;
+    return SMB200_OK;
+}
+
+smb200_status smb200_comm_destroy(smb200_ctx* ctx) {
+    if (!ctx || !ctx->comm) return SMB200_OK;
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->aux_stream);
+    g_nccl.CommDestroy((ncclComm_t)ctx->comm);
+    ctx->comm = nullptr;
+    ctx->world = 1;
+    ctx->rank = 0;
+    return SMB200_OK;
+}
+
+smb200_status smb200_dist_free(smb200_dist* d) {
+    if (!d) return SMB200_OK;
+    cudaSetDevice(d->ctx->device);
+    cudaStreamSynchronize(d->ctx->stream);
+    cudaStreamSynchronize(d->ctx->aux_stream);
+    plan_free(d->plan_int);
+    plan_free(d->plan_lo);
+    plan_free(d->plan_hi);
+    if (d->send_idx) cudaFree(d->send_idx);
+    if (d->send_buf) cudaFree(d->send_buf);
+    if (d->local) smb200_crs_free(d->local);
+    delete d;
+    return SMB200_OK;
+}
+
+smb200_status smb200_dist_create(smb200_ctx* ctx, smb200_vtype vt, smb200_itype it, uint64_t n_global, const uint64_t* bounds,
+                                 uint64_t nnz_local, const void* values, const void* columns_global,
+                                 const void* offset_rows_local, smb200_dist** out) {
+    SMB_REQUIRE(ctx && bounds && out, SMB200_ERR_INVALID, "dist_create: NULL argument");
+    SMB_REQUIRE(ctx->world == 1 || ctx->comm, SMB200_ERR_INVALID, "dist_create: call smb200_comm_init first");
+    const int world = ctx->world, me = ctx->rank;
+    SMB_REQUIRE(bounds[world] == n_global && bounds[0] == 0, SMB200_ERR_INVALID, "dist_create: bounds must span [0, n_global]");
+    *out = nullptr;
+    smb200_dist* d = new smb200_dist();
+    d->ctx = ctx; d->vt = vt; d->it = it; d->n_global = n_global;
+    d->bounds.assign(bounds, bounds + world + 1);
+    d->row_lo = bounds[me];
+    d->n_local = bounds[me + 1] - bounds[me];
+    // ghost plan on the host (partition.cpp)
+    uint64_t n_ghost = 0;
+    d->recv_count.assign(world, 0);
+    smb200_status s = smb200_ghost_plan(it, nnz_local, columns_global, (uint32_t)world, (uint32_t)me, bounds, nullptr, nullptr, &n_ghost, d->recv_count.data());
+    std::vector<uint64_t> ghosts(n_ghost);
+    std::vector<unsigned char> cols_local(nnz_local * isize(it));
+    if (s == SMB200_OK)
+        s = smb200_ghost_plan(it, nnz_local, columns_global, (uint32_t)world, (uint32_t)me, bounds, cols_local.data(), ghosts.data(), &n_ghost, d->recv_count.data());
+    if (s != SMB200_OK) { delete d; return s; }
+    d->n_ghost = n_ghost;
+    d->recv_count[me] = 0;
+    s = smb200_crs_upload(ctx, vt, it, d->n_local, d->n_local + n_ghost, nnz_local, values, cols_local.data(), offset_rows_local, &d->local);
+    if (s != SMB200_OK) { delete d; return s; }
+    d->local->x_extra = n_ghost;
+    // interior = longest run of rows without ghost references
+    {
+        uint64_t best_b = 0, best_e = 0, run_b = 0;
+        auto off = [&](uint64_t r) { return it == SMB200_U64 ? ((const uint64_t*)offset_rows_local)[r] : (uint64_t)((const uint32_t*)offset_rows_local)[r]; };
+        auto col = [&](uint64_t k) { return it == SMB200_U64 ? ((const uint64_t*)cols_local.data())[k] : (uint64_t)((const uint32_t*)cols_local.data())[k]; };
+        for (uint64_t r = 0; r < d->n_local; ++r) {
+            bool ghost = false;
+            for (uint64_t k = off(r); k < off(r + 1) && !ghost; ++k) ghost = col(k) >= d->n_local;
+            if (ghost) { if (r - run_b > best_e - best_b) { best_b = run_b; best_e = r; } run_b = r + 1; }
+        }
+        if (d->n_local - run_b > best_e - best_b) { best_b = run_b; best_e = d->n_local; }
+        d->int_begin = best_b; d->int_end = best_e;
+    }
+    s = dist_setup_exchange(d, ghosts);
+    if (s == SMB200_OK) s = dist_build_plans(d);
+    if (s != SMB200_OK) { smb200_dist_free(d); return s; }
+    *out = d;
+    return SMB200_OK;
+}
+
+smb200_status smb200_dist_laplace(smb200_ctx* ctx, smb200_vtype vt, smb200_itype it, uint64_t nx, uint64_t ny, uint64_t nz,
+                                  smb200_dist** out) {
+    SMB_REQUIRE(ctx && out, SMB200_ERR_INVALID, "dist_laplace: NULL argument");
+    SMB_REQUIRE(ctx->world == 1 || ctx->comm, SMB200_ERR_INVALID, "dist_laplace: call smb200_comm_init first");
+    SMB_REQUIRE(nx && ny && nz, SMB200_ERR_INVALID, "dist_laplace: empty grid");
+    const int world = ctx->world, me = ctx->rank;
+    const uint64_t plane = nx * ny, N = plane * nz;
+    SMB_REQUIRE(nz >= (uint64_t)world, SMB200_ERR_INVALID, "dist_laplace: fewer z-planes (%llu) than ranks (%d)", (unsigned long long)nz, world);
+    *out = nullptr;
+    smb200_dist* d = new smb200_dist();
+    d->ctx = ctx; d->vt = vt; d->it = it; d->n_global = N;
+    d->bounds.resize(world + 1);
+    // whole z-planes per rank, as even as possible
+    for (int q = 0; q <= world; ++q) d->bounds[q] = (nz * (uint64_t)q / (uint64_t)world) * plane;
+    d->row_lo = d->bounds[me];
+    d->n_local = d->bounds[me + 1] - d->bounds[me];
+    const uint64_t n_lo = (nz > 1 && me > 0) ? plane : 0, n_hi = (nz > 1 && me + 1 < world) ? plane : 0;
+    d->n_ghost = n_lo + n_hi;
+    smb200_status s = gen_laplace_block(ctx, vt, it, nx, ny, nz, d->row_lo, d->row_lo + d->n_local, 1, n_lo, d->n_local + d->n_ghost, &d->local);
+    if (s != SMB200_OK) { delete d; return s; }
+    d->local->x_extra = d->n_ghost;
+    d->recv_count.assign(world, 0);
+    d->recv_off.assign(world, 0);
+    d->send_count.assign(world, 0);
+    d->send_off.assign(world, 0);
+    d->send_contig.assign(world, 0);
+    d->send_first.assign(world, 0);
+    if (n_lo) { d->recv_count[me - 1] = plane; d->recv_off[me - 1] = 0; d->send_count[me - 1] = plane; d->send_contig[me - 1] = 1; d->send_first[me - 1] = 0; }
+    if (n_hi) { d->recv_count[me + 1] = plane; d->recv_off[me + 1] = n_lo; d->send_count[me + 1] = plane; d->send_contig[me + 1] = 1; d->send_first[me + 1] = d->n_local - plane; }
+    d->total_send = n_lo + n_hi;
+    d->int_begin = std::min<uint64_t>(n_lo, d->n_local);
+    d->int_end = std::max<uint64_t>(d->int_begin, d->n_local - std::min<uint64_t>(n_hi, d->n_local));
+    s = dist_build_plans(d);
+    if (s != SMB200_OK) { smb200_dist_free(d); return s; }
+    *out = d;
+    return SMB200_OK;
+}
+
+smb200_status smb200_dist_dims(const smb200_dist* d, uint64_t* out4) {
+    SMB_REQUIRE(d && out4, SMB200_ERR_INVALID, "dist_dims: NULL argument");
+    out4[0] = d->n_local; out4[1] = d->n_ghost; out4[2] = d->local->nnz; out4[3] = d->row_lo;
+    return SMB200_OK;
+}
+
+smb200_status smb200_dist_local(smb200_dist* d, smb200_crs** out) {
+    SMB_REQUIRE(d && out, SMB200_ERR_INVALID, "dist_local: NULL argument");
+    *out = d->local;
+    return SMB200_OK;
+}
+
+smb200_status smb200_dist_vec_create(smb200_dist* d, smb200_vec** out) {
+    SMB_REQUIRE(d && out, SMB200_ERR_INVALID, "dist_vec_create: NULL argument");
+    return vec_create_cap(d->ctx, d->vt, d->n_local, d->n_local + d->n_ghost, out);
+}
+
+smb200_status smb200_dist_spmv(smb200_dist* d, smb200_vec* x, smb200_vec* y) {
+    SMB_REQUIRE(d && x && y, SMB200_ERR_INVALID, "dist_spmv: NULL argument");
+    SMB_REQUIRE(x->vt == d->vt && y->vt == d->vt, SMB200_ERR_INVALID, "dist_spmv: value types differ");
+    SMB_REQUIRE(x->n >= d->n_local && x->cap >= d->n_local + d->n_ghost, SMB200_ERR_DIM,
+                "Dimension mismatch: x must come from smb200_dist_vec_create (room for %llu ghosts)", (unsigned long long)d->n_ghost);
+    SMB_REQUIRE(y->n >= d->n_local, SMB200_ERR_DIM, "Dimension mismatch");
+    SMB_REQUIRE(x->d != y->d, SMB200_ERR_INVALID, "dist_spmv: x and y alias");
+    return dist_spmv_impl(d, x->d, y->d, nullptr);
+}
+
+smb200_status smb200_dist_dot(smb200_dist* d, const smb200_vec* x, const smb200_vec* y, double* out) {
+    SMB_REQUIRE(d && x && y && out, SMB200_ERR_INVALID, "dist_dot: NULL argument");
+    SMB_REQUIRE(x->vt == d->vt && y->vt == d->vt, SMB200_ERR_INVALID, "dist_dot: value types differ");
+    smb200_ctx* ctx = d->ctx;
+    const uint64_t n = std::min(x->n, y->n);
+    SMB_TRY(dot_launch(ctx, d->vt, x->d, y->d, n, 2));
+    if (ctx->world > 1)
+        SMB_NCCL(g_nccl.AllReduce(ctx->red_result + 2, ctx->red_result + 2, 1, kNcclFloat64, kNcclSum, (ncclComm_t)ctx->comm, ctx->stream));
+    SMB_TRY(fetch_result(ctx, 2, out));
+    if (d->vt == SMB200_F32) *out = (double)(float)*out;
+    return SMB200_OK;
+}
+
+smb200_status smb200_dist_cg_solve(smb200_dist* d, const smb200_vec* b, smb200_vec* x, double tol, int32_t relative,
+                                   uint64_t iter_max, smb200_cg_stats* stats) {
+    SMB_REQUIRE(d && b && x, SMB200_ERR_INVALID, "dist_cg_solve: NULL argument");
+    SMB_REQUIRE(b->vt == d->vt && x->vt == d->vt, SMB200_ERR_INVALID, "dist_cg_solve: value types differ");
+    SMB_REQUIRE(d->n_local == b->n && d->n_local == x->n, SMB200_ERR_SIZE_MISMATCH, "Matrix and vector size mismatch");
+    SMB_REQUIRE(x->cap >= d->n_local + d->n_ghost, SMB200_ERR_DIM, "Dimension mismatch: x must come from smb200_dist_vec_create");
+    smb200_ctx* ctx = d->ctx;
+    smb200_crs* a = d->local;
+    CgWork& w = a->cg;
+    const uint64_t n = d->n_local;
+    const uint64_t launches0 = g_launches;
+    const bool multi = ctx->world > 1;
+    ncclComm_t comm = (ncclComm_t)ctx->comm;
+    if (stats) memset(stats, 0, sizeof *stats);
+    SMB_CUDA(cudaSetDevice(ctx->device));
+    SMB_TRY(cg_prepare(ctx, w, d->vt, n, n + d->n_ghost, iter_max));
+    double* S = w.scalars;
+    enum { S_RR = 0, S_PAP = 1, S_RR_NEW = 4, S_THRESH = 5, S_ITER = 6, S_DONE = 7, S_COUNT = 8 };
+
+    double threshold = tol;
+    if (relative) {
+        double bb = 0.0;
+        SMB_TRY(smb200_dist_dot(d, b, b, &bb));
+        threshold = tol * sqrt(bb);
+    }
+    cudaEvent_t ev0, ev1;
+    SMB_CUDA(cudaEventCreate(&ev0));
+    SMB_CUDA(cudaEventCreate(&ev1));
+    SMB_CUDA(cudaEventRecord(ev0, ctx->stream));
+    double init[S_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0};
+    init[S_THRESH] = threshold;
+    memcpy(w.scalars_host + 3 * S_COUNT, init, sizeof init);
+    SMB_CUDA(cudaMemcpyAsync(S, w.scalars_host + 3 * S_COUNT, sizeof init, cudaMemcpyHostToDevice, ctx->stream));
+    // r = b - A x ; p = r ; rr = r.r
+    SMB_TRY(dist_spmv_impl(d, x->d, w.ap, nullptr));
+    SMB_TRY(cg_init_launch(ctx, w, d->vt, b->d, n));
+    if (multi) SMB_NCCL(g_nccl.AllReduce(S + S_RR_NEW, S + S_RR_NEW, 1, kNcclFloat64, kNcclSum, comm, ctx->stream));
+
+    const int batch = 8;
+    cudaEvent_t poll_ev[2];
+    SMB_CUDA(cudaEventCreateWithFlags(&poll_ev[0], cudaEventDisableTiming));
+    SMB_CUDA(cudaEventCreateWithFlags(&poll_ev[1], cudaEventDisableTiming));
+    smb200_status st = SMB200_OK;
+    uint64_t launched = 0, rounds = 0;
+    bool finished = false;
+    while (st == SMB200_OK && !finished) {
+        const int slot = (int)(rounds & 1);
+        cudaError_t e = cudaMemcpyAsync(w.scalars_host + slot * S_COUNT, S, S_COUNT * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaEventRecord(poll_ev[slot], ctx->stream);
+        if (e != cudaSuccess) { set_error("dist_cg_solve: %s", cudaGetErrorString(e)); st = SMB200_ERR_CUDA; break; }
+        const uint64_t nb = std::min<uint64_t>(iter_max - launched, (uint64_t)batch);
+        for (uint64_t k = 0; k < nb && st == SMB200_OK; ++k) {
+            // every rank runs the same number of launches: the stop flag is derived from all-reduced
+            // values, hence identical everywhere, and finished iterations exit early on the device
+            if (multi && cudaMemsetAsync(S + S_PAP, 0, 3 * sizeof(double), ctx->stream) != cudaSuccess) { set_error("dist_cg_solve: memset failed"); st = SMB200_ERR_CUDA; break; }
+            st = dist_spmv_impl(d, w.p, w.ap, S);
+            if (st == SMB200_OK && multi && g_nccl.AllReduce(S + S_PAP, S + S_PAP, 3, kNcclFloat64, kNcclSum, comm, ctx->stream) != 0) { set_error("dist_cg_solve: all-reduce failed"); st = SMB200_ERR_NCCL; }
+            if (st == SMB200_OK) st = cg_xr_launch(ctx, w, d->vt, x->d, n);
+            if (st == SMB200_OK && multi && g_nccl.AllReduce(S + S_RR_NEW, S + S_RR_NEW, 1, kNcclFloat64, kNcclSum, comm, ctx->stream) != 0) { set_error("dist_cg_solve: all-reduce failed"); st = SMB200_ERR_NCCL; }
+            if (st == SMB200_OK) st = cg_p_launch(ctx, w, d->vt, n);
+        }
+        if (st != SMB200_OK) break;
+        launched += nb;
+        e = cudaEventSynchronize(poll_ev[slot]);
+        if (e != cudaSuccess) { set_error("dist_cg_solve: %s", cudaGetErrorString(e)); st = SMB200_ERR_CUDA; break; }
+        if (w.scalars_host[slot * S_COUNT + S_DONE] != 0.0 || nb == 0) finished = true;
+        ++rounds;
+    }
+    if (st == SMB200_OK) {
+        cudaError_t e = cudaEventRecord(ev1, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(w.scalars_host, S, S_COUNT * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { set_error("dist_cg_solve: %s", cudaGetErrorString(e)); st = SMB200_ERR_CUDA; }
+    }
+    if (st == SMB200_OK && stats) {
+        const double* H = w.scalars_host;
+        stats->iterations = (uint64_t)H[S_ITER];
+        stats->final_residual = sqrt(H[S_RR_NEW]);
+        stats->converged = H[S_DONE] != 0.0;
+        cudaEventElapsedTime(&stats->device_ms, ev0, ev1);
+        stats->launches = g_launches - launches0;
+    }
+    if (st != SMB200_OK) cudaStreamSynchronize(ctx->stream);
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+    cudaEventDestroy(poll_ev[0]); cudaEventDestroy(poll_ev[1]);
+    return st;
+}
+
+}  // extern "C"

@@ -1,0 +1,776 @@
+// THE hot path: y = A x for a CRS matrix (SparseMatrix::mvp, sparsematrix.rs:146-158, over
+// SparseMatCRS::iter_row, sparsemat_crs.rs:102-110).
+//
+// Roofline: HBM.  Algorithmic bytes per launch
+//     B = nnz*(sizeof T + sizeof I) + (n_rows+1)*sizeof I + n_cols*sizeof T + n_rows*sizeof T
+// (values and columns streamed once, offsets once, x once — its re-use is served by L1/L2 —, y once).
+//
+// Kernel families:
+//   K1/K2  spmv_vector_kernel<LANES>   LANES threads per row (1 = scalar, 2..16 = sub-warp, 32 = warp),
+//                                      shuffle reduction; LANES is chosen from the mean row length.
+//   K3     spmv_stream_kernel          "merge-path, row-snapped": CTA k owns the rows whose merge
+//                                      coordinate row + offset_rows[row] falls into [k*TARGET,(k+1)*TARGET),
+//                                      i.e. an equal share of rows + non-zeros.  The CTA streams its
+//                                      contiguous slice of values/columns with 128-bit loads, multiplies
+//                                      by the gathered x on the fly, parks the products in shared memory
+//                                      and then sums every row in STORAGE ORDER with one thread per row.
+//                                      Rows of <= 64 non-zeros therefore reproduce the reference's
+//                                      sequential `sum += x[col]*val` bit for bit; longer rows use a
+//                                      warp (or the CTA) and fall under the documented tolerance.
+//   K3-TMA spmv_stream_tma_kernel      same, but the slice is brought in by two cp.async.bulk (TMA)
+//                                      copies completing on an mbarrier; products overwrite the values.
+//   K4     spmv_banded_kernel          K3-TMA plus the block's x window [cmin,cmax] staged in shared
+//                                      memory by a third bulk copy (banded / 2-D stencil matrices);
+//          SMB200_FLAG_L2_PERSIST_X    L2 access-policy window over x for everything else.
+// Every variant can fuse a dot product  sum_r w[r]*y[r]  into its epilogue (K7a, used by CG).
+#include "common.cuh"
+#include "reduce.cuh"
+
+#include <cstdlib>
+
+namespace smb {
+
+constexpr int kSpmvThreads = 256;
+constexpr int kWarpRowMin = 64;      // rows longer than this are reduced by a warp inside the stream kernels
+constexpr int kBigRow = 1024;        // fallback path: rows at least this long are reduced by the whole CTA
+constexpr int kLongCap = 96;         // per-CTA list of rows deferred to the warp / CTA pass
+
+struct DotArgs {
+    const void* w;            // weights (nullptr = no fused dot)
+    double* partials;
+    unsigned int* ticket;
+    double* result;
+    // CG plumbing (cg.cu): the CTA that finishes last also rolls rr <- rr_new, and every CTA leaves
+    // at once when the solver's stop flag is already set.
+    double* roll_dst;
+    const double* roll_src;
+    const double* done;
+};
+
+template <class T> __device__ __forceinline__ T warp_sum_t(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = add_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+template <class T>
+__device__ __forceinline__ void finish_dot(double acc, const DotArgs& d) {
+    __shared__ double scratch[kSpmvThreads / 32 + 1];
+    const double bsum = block_sum<kSpmvThreads>(acc, scratch);
+    double total;
+    if (grid_sum<kSpmvThreads>(bsum, d.partials, d.ticket, scratch, total))
+        if (threadIdx.x == 0) {
+            *d.result = (double)(T)total;
+            if (d.roll_dst) *d.roll_dst = *d.roll_src;
+        }
+}
+__device__ __forceinline__ bool solver_done(const DotArgs& d) { return d.done != nullptr && __ldcg(d.done) != 0.0; }
+
+// ---- K1 / K2: LANES threads per row -----------------------------------------------------------------
+template <class T, class I, int LANES, bool DOT>
+__global__ void __launch_bounds__(kSpmvThreads)
+spmv_vector_kernel(const T* __restrict__ vals, const I* __restrict__ cols, const I* __restrict__ offs,
+                   uint64_t row_begin, uint64_t row_end, const T* __restrict__ x, T* __restrict__ y, DotArgs dot) {
+    constexpr int ROWS = kSpmvThreads / LANES;
+    if constexpr (DOT) { if (solver_done(dot)) return; }
+    const uint64_t row = row_begin + (uint64_t)blockIdx.x * ROWS + threadIdx.x / LANES;
+    const int sub = threadIdx.x % LANES;
+    double acc = 0.0;
+    T s = T(0);
+    if (row < row_end) {
+        const uint64_t a = (uint64_t)__ldg(offs + row), e = (uint64_t)__ldg(offs + row + 1);
+        for (uint64_t k = a + sub; k < e; k += LANES)
+            s = add_rn(s, mul_rn(__ldg(x + (size_t)__ldcs(cols + k)), __ldcs(vals + k)));
+    }
+#pragma unroll
+    for (int o = LANES / 2; o > 0; o >>= 1) s = add_rn(s, __shfl_xor_sync(0xffffffffu, s, o));
+    if (row < row_end && sub == 0) {
+        y[row] = s;
+        if constexpr (DOT) acc = (double)mul_rn(__ldg((const T*)dot.w + row), s);
+    }
+    if constexpr (DOT) finish_dot<T>(acc, dot);
+}
+
+// ---- shared pieces of the stream kernels ------------------------------------------------------------
+// 4 consecutive elements of an array, 16-byte (T,I of 4 bytes) or 32-byte (8 bytes) aligned.
+template <class E> struct Quad { E e[4]; };
+
+template <class E> __device__ __forceinline__ Quad<E> load_quad_stream(const E* p) {
+    Quad<E> q;
+    if constexpr (sizeof(E) == 4) {
+        const uint4 v = __ldcs(reinterpret_cast<const uint4*>(p));
+        memcpy(q.e, &v, 16);
+    } else {
+        const uint4 v0 = __ldcs(reinterpret_cast<const uint4*>(p));
+        const uint4 v1 = __ldcs(reinterpret_cast<const uint4*>(p) + 1);
+        memcpy(q.e, &v0, 16);
+        memcpy(q.e + 2, &v1, 16);
+    }
+    return q;
+}
+template <class E> __device__ __forceinline__ Quad<E> load_quad_shared(const E* p) {
+    Quad<E> q;
+    if constexpr (sizeof(E) == 4) {
+        const uint4 v = *reinterpret_cast<const uint4*>(p);
+        memcpy(q.e, &v, 16);
+    } else {
+        const uint4 v0 = *reinterpret_cast<const uint4*>(p);
+        const uint4 v1 = *(reinterpret_cast<const uint4*>(p) + 1);
+        memcpy(q.e, &v0, 16);
+        memcpy(q.e + 2, &v1, 16);
+    }
+    return q;
+}
+template <class E> __device__ __forceinline__ void store_quad_shared(E* p, const Quad<E>& q) {
+    if constexpr (sizeof(E) == 4) {
+        uint4 v; memcpy(&v, q.e, 16);
+        *reinterpret_cast<uint4*>(p) = v;
+    } else {
+        uint4 v0, v1; memcpy(&v0, q.e, 16); memcpy(&v1, q.e + 2, 16);
+        *reinterpret_cast<uint4*>(p) = v0;
+        *(reinterpret_cast<uint4*>(p) + 1) = v1;
+    }
+}
+
+// Row sums out of the staged products.  prod[k] holds the product of element a0 + k.
+// Pass 1: one thread per row, storage order (bit-exact).  Pass 2: rows longer than kWarpRowMin, a warp each.
+template <class T, class I, bool DOT>
+__device__ __forceinline__ double reduce_rows_from_smem(const T* prod, const I* __restrict__ offs, uint64_t r0, uint64_t r1,
+                                                        uint64_t a0, T* __restrict__ y, const T* __restrict__ w,
+                                                        unsigned int* s_long_count, unsigned int* s_long_rows) {
+    double acc = 0.0;
+    for (uint64_t r = r0 + threadIdx.x; r < r1; r += kSpmvThreads) {
+        const unsigned a = (unsigned)((uint64_t)__ldg(offs + r) - a0);
+        const unsigned e = (unsigned)((uint64_t)__ldg(offs + r + 1) - a0);
+        if (e - a <= (unsigned)kWarpRowMin) {
+            T s = T(0);
+            for (unsigned k = a; k < e; ++k) s = add_rn(s, prod[k]);
+            y[r] = s;
+            if constexpr (DOT) acc += (double)mul_rn(__ldg(w + r), s);
+        } else {
+            const unsigned slot = atomicAdd(s_long_count, 1u);
+            s_long_rows[slot] = (unsigned)(r - r0);
+        }
+    }
+    __syncthreads();
+    const unsigned n_long = *s_long_count;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (unsigned j = warp; j < n_long; j += kSpmvThreads / 32) {
+        const uint64_t r = r0 + s_long_rows[j];
+        const unsigned a = (unsigned)((uint64_t)__ldg(offs + r) - a0);
+        const unsigned e = (unsigned)((uint64_t)__ldg(offs + r + 1) - a0);
+        T s = T(0);
+        for (unsigned k = a + lane; k < e; k += 32) s = add_rn(s, prod[k]);
+        s = warp_sum_t(s);
+        if (lane == 0) {
+            y[r] = s;
+            if constexpr (DOT) acc += (double)mul_rn(__ldg(w + r), s);
+        }
+    }
+    return acc;
+}
+
+// Blocks whose slice does not fit the staging buffer (they contain a very long row): classic
+// CSR-vector inside the CTA — a warp per row, the whole CTA for rows >= kBigRow.
+template <class T, class I, bool DOT>
+__device__ __forceinline__ double rows_direct(const T* __restrict__ vals, const I* __restrict__ cols, const I* __restrict__ offs,
+                                              uint64_t r0, uint64_t r1, const T* __restrict__ x, T* __restrict__ y,
+                                              const T* __restrict__ w, unsigned int* s_long_count, unsigned int* s_long_rows,
+                                              double* scratch) {
+    double acc = 0.0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint64_t r = r0 + warp; r < r1; r += kSpmvThreads / 32) {
+        const uint64_t a = (uint64_t)__ldg(offs + r), e = (uint64_t)__ldg(offs + r + 1);
+        if (e - a >= (uint64_t)kBigRow) {
+            if (lane == 0) {
+                const unsigned slot = atomicAdd(s_long_count, 1u);
+                if (slot < (unsigned)kLongCap) s_long_rows[slot] = (unsigned)(r - r0);
+            }
+            continue;
+        }
+        T s = T(0);
+        for (uint64_t k = a + lane; k < e; k += 32) s = add_rn(s, mul_rn(__ldg(x + (size_t)__ldcs(cols + k)), __ldcs(vals + k)));
+        s = warp_sum_t(s);
+        if (lane == 0) {
+            y[r] = s;
+            if constexpr (DOT) acc += (double)mul_rn(__ldg(w + r), s);
+        }
+    }
+    __syncthreads();
+    const unsigned n_big = min(*s_long_count, (unsigned)kLongCap);
+    for (unsigned j = 0; j < n_big; ++j) {
+        const uint64_t r = r0 + s_long_rows[j];
+        const uint64_t a = (uint64_t)__ldg(offs + r), e = (uint64_t)__ldg(offs + r + 1);
+        T s0 = T(0), s1 = T(0);
+        uint64_t k = a + threadIdx.x;
+        for (; k + kSpmvThreads < e; k += 2 * kSpmvThreads) {
+            const T p0 = mul_rn(__ldg(x + (size_t)__ldcs(cols + k)), __ldcs(vals + k));
+            const T p1 = mul_rn(__ldg(x + (size_t)__ldcs(cols + k + kSpmvThreads)), __ldcs(vals + k + kSpmvThreads));
+            s0 = add_rn(s0, p0);
+            s1 = add_rn(s1, p1);
+        }
+        if (k < e) s0 = add_rn(s0, mul_rn(__ldg(x + (size_t)__ldcs(cols + k)), __ldcs(vals + k)));
+        const double tot = block_sum<kSpmvThreads>((double)s0 + (double)s1, scratch);
+        if (threadIdx.x == 0) {
+            const T s = (T)tot;
+            y[r] = s;
+            if constexpr (DOT) acc += (double)mul_rn(__ldg(w + r), s);
+        }
+    }
+    return acc;
+}
+
+// ---- K3: stream kernel, register-staged 128-bit loads -----------------------------------------------
+template <class T, class I, bool DOT>
+__global__ void __launch_bounds__(kSpmvThreads)
+spmv_stream_kernel(const T* __restrict__ vals, const I* __restrict__ cols, const I* __restrict__ offs,
+                   const I* __restrict__ blk_rows, unsigned cap, const T* __restrict__ x, T* __restrict__ y, DotArgs dot) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    T* prod = reinterpret_cast<T*>(smem_raw);
+    __shared__ unsigned int s_long_count;
+    __shared__ unsigned int s_long_rows[kLongCap];
+    __shared__ double scratch[kSpmvThreads / 32 + 1];
+    if constexpr (DOT) { if (solver_done(dot)) return; }
+    if (threadIdx.x == 0) s_long_count = 0;
+    const uint64_t r0 = (uint64_t)__ldg(blk_rows + blockIdx.x), r1 = (uint64_t)__ldg(blk_rows + blockIdx.x + 1);
+    const uint64_t n0 = (uint64_t)__ldg(offs + r0), n1 = (uint64_t)__ldg(offs + r1);
+    const uint64_t a0 = n0 & ~(uint64_t)3;
+    double acc = 0.0;
+    __syncthreads();
+    if (n1 - a0 <= (uint64_t)cap) {
+        const unsigned groups = (unsigned)((n1 - a0 + 3) >> 2);
+        const T* vbase = vals + a0;
+        const I* cbase = cols + a0;
+        unsigned g = threadIdx.x;
+        // two quads in flight per thread: all streaming loads first, then the gathers
+        for (; g + kSpmvThreads < groups; g += 2 * kSpmvThreads) {
+            const Quad<I> c0 = load_quad_stream(cbase + 4 * (size_t)g);
+            const Quad<I> c1 = load_quad_stream(cbase + 4 * (size_t)(g + kSpmvThreads));
+            const Quad<T> v0 = load_quad_stream(vbase + 4 * (size_t)g);
+            const Quad<T> v1 = load_quad_stream(vbase + 4 * (size_t)(g + kSpmvThreads));
+            Quad<T> p0, p1;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) p0.e[k] = __ldg(x + (size_t)c0.e[k]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) p1.e[k] = __ldg(x + (size_t)c1.e[k]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { p0.e[k] = mul_rn(p0.e[k], v0.e[k]); p1.e[k] = mul_rn(p1.e[k], v1.e[k]); }
+            store_quad_shared(prod + 4 * g, p0);
+            store_quad_shared(prod + 4 * (g + kSpmvThreads), p1);
+        }
+        if (g < groups) {
+            const Quad<I> c0 = load_quad_stream(cbase + 4 * (size_t)g);
+            const Quad<T> v0 = load_quad_stream(vbase + 4 * (size_t)g);
+            Quad<T> p0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) p0.e[k] = mul_rn(__ldg(x + (size_t)c0.e[k]), v0.e[k]);
+            store_quad_shared(prod + 4 * g, p0);
+        }
+        __syncthreads();
+        acc = reduce_rows_from_smem<T, I, DOT>(prod, offs, r0, r1, a0, y, (const T*)dot.w, &s_long_count, s_long_rows);
+    } else {
+        acc = rows_direct<T, I, DOT>(vals, cols, offs, r0, r1, x, y, (const T*)dot.w, &s_long_count, s_long_rows, scratch);
+    }
+    if constexpr (DOT) finish_dot<T>(acc, dot);
+}
+
+// ---- TMA helpers (cp.async.bulk + mbarrier) ---------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared bulk copy; size and both addresses are multiples of 16 bytes
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ---- K3-TMA / K4: slice (and optionally the x window) brought in by bulk copies ----------------------
+template <class T, class I, bool DOT, bool XWIN>
+__global__ void __launch_bounds__(kSpmvThreads)
+spmv_stream_tma_kernel(const T* __restrict__ vals, const I* __restrict__ cols, const I* __restrict__ offs,
+                       const I* __restrict__ blk_rows, const I* __restrict__ blk_win, unsigned cap, unsigned win_cap,
+                       const T* __restrict__ x, T* __restrict__ y, DotArgs dot) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    // layout: [values/products: cap*sizeof T][columns: cap*sizeof I][x window: win_cap*sizeof T]
+    T* sv = reinterpret_cast<T*>(smem_raw);
+    I* sc = reinterpret_cast<I*>(smem_raw + (size_t)cap * sizeof(T));
+    T* sx = reinterpret_cast<T*>(smem_raw + (size_t)cap * (sizeof(T) + sizeof(I)));
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ unsigned int s_long_count;
+    __shared__ unsigned int s_long_rows[kLongCap];
+    __shared__ double scratch[kSpmvThreads / 32 + 1];
+    if constexpr (DOT) { if (solver_done(dot)) return; }
+    const uint64_t r0 = (uint64_t)__ldg(blk_rows + blockIdx.x), r1 = (uint64_t)__ldg(blk_rows + blockIdx.x + 1);
+    const uint64_t n0 = (uint64_t)__ldg(offs + r0), n1 = (uint64_t)__ldg(offs + r1);
+    const uint64_t a0 = n0 & ~(uint64_t)3;
+    const unsigned count = (unsigned)(((n1 - a0) + 3) & ~(uint64_t)3);
+    uint64_t w0 = 0;          // first x element of the window (aligned down to 16 bytes)
+    unsigned wcount = 0;
+    bool fits = (n1 - a0) <= (uint64_t)cap;
+    if constexpr (XWIN) {
+        const uint64_t cmin = (uint64_t)__ldg(blk_win + 2 * (size_t)blockIdx.x);
+        const uint64_t cend = (uint64_t)__ldg(blk_win + 2 * (size_t)blockIdx.x + 1);
+        constexpr uint64_t XA = 16 / sizeof(T);
+        w0 = cmin & ~(XA - 1);
+        const uint64_t wc = cend > w0 ? ((cend - w0 + XA - 1) & ~(XA - 1)) : 0;
+        fits = fits && wc <= (uint64_t)win_cap;
+        wcount = (unsigned)wc;
+    }
+    if (threadIdx.x == 0) {
+        s_long_count = 0;
+        mbar_init(&bar, 1);
+    }
+    __syncthreads();
+    double acc = 0.0;
+    if (fits) {
+        if (threadIdx.x == 0) {
+            unsigned bytes = count * (unsigned)(sizeof(T) + sizeof(I));
+            if constexpr (XWIN) bytes += wcount * (unsigned)sizeof(T);
+            mbar_expect_tx(&bar, bytes);
+            bulk_g2s(sc, cols + a0, count * (unsigned)sizeof(I), &bar);
+            bulk_g2s(sv, vals + a0, count * (unsigned)sizeof(T), &bar);
+            if constexpr (XWIN) { if (wcount) bulk_g2s(sx, x + w0, wcount * (unsigned)sizeof(T), &bar); }
+        }
+        mbar_wait(&bar, 0);
+        const unsigned groups = count >> 2;
+        for (unsigned g = threadIdx.x; g < groups; g += kSpmvThreads) {
+            const Quad<I> c = load_quad_shared(sc + 4 * g);
+            Quad<T> v = load_quad_shared(sv + 4 * g);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                T xv;
+                if constexpr (XWIN) {
+                    // elements outside [n0,n1) belong to neighbouring blocks: their columns may lie
+                    // outside this block's window, so clamp (their products are never read)
+                    const uint64_t rel = (uint64_t)c.e[k] - w0;
+                    xv = sx[rel < (uint64_t)wcount ? rel : 0];
+                } else {
+                    xv = __ldg(x + (size_t)c.e[k]);
+                }
+                v.e[k] = mul_rn(xv, v.e[k]);
+            }
+            store_quad_shared(sv + 4 * g, v);
+        }
+        __syncthreads();
+        acc = reduce_rows_from_smem<T, I, DOT>(sv, offs, r0, r1, a0, y, (const T*)dot.w, &s_long_count, s_long_rows);
+    } else {
+        acc = rows_direct<T, I, DOT>(vals, cols, offs, r0, r1, x, y, (const T*)dot.w, &s_long_count, s_long_rows, scratch);
+    }
+    if constexpr (DOT) finish_dot<T>(acc, dot);
+}
+
+// ---- plan construction --------------------------------------------------------------------------------
+// Split points of the merge coordinate key(r) = (r - rb) + (offs[r] - offs[rb]) at multiples of `target`.
+template <class I>
+__global__ void split_rows_kernel(const I* __restrict__ offs, uint64_t rb, uint64_t re, uint64_t target, uint64_t n_blocks,
+                                  I* __restrict__ blk_rows) {
+    const uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (k > n_blocks) return;
+    if (k == n_blocks) { blk_rows[k] = (I)re; return; }
+    const uint64_t base = (uint64_t)offs[rb];
+    const uint64_t want = k * target;
+    uint64_t lo = rb, hi = re;          // smallest r in [rb,re] with key(r) >= want
+    while (lo < hi) {
+        const uint64_t mid = lo + ((hi - lo) >> 1);
+        const uint64_t key = (mid - rb) + ((uint64_t)offs[mid] - base);
+        if (key < want) lo = mid + 1; else hi = mid;
+    }
+    blk_rows[k] = (I)lo;
+}
+
+// Per block: [min column, max column + 1) over the block's own elements.
+template <class I>
+__global__ void __launch_bounds__(kSpmvThreads)
+block_window_kernel(const I* __restrict__ cols, const I* __restrict__ offs, const I* __restrict__ blk_rows,
+                    I* __restrict__ blk_win, unsigned long long* __restrict__ max_win) {
+    __shared__ unsigned long long s_min[kSpmvThreads / 32], s_max[kSpmvThreads / 32];
+    const uint64_t r0 = (uint64_t)blk_rows[blockIdx.x], r1 = (uint64_t)blk_rows[blockIdx.x + 1];
+    const uint64_t n0 = (uint64_t)offs[r0], n1 = (uint64_t)offs[r1];
+    unsigned long long mn = ~0ull, mx = 0ull;
+    for (uint64_t k = n0 + threadIdx.x; k < n1; k += kSpmvThreads) {
+        const unsigned long long c = (unsigned long long)cols[k];
+        mn = c < mn ? c : mn;
+        mx = c + 1 > mx ? c + 1 : mx;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long a = __shfl_xor_sync(0xffffffffu, mn, o), b = __shfl_xor_sync(0xffffffffu, mx, o);
+        mn = a < mn ? a : mn;
+        mx = b > mx ? b : mx;
+    }
+    if ((threadIdx.x & 31) == 0) { s_min[threadIdx.x >> 5] = mn; s_max[threadIdx.x >> 5] = mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < kSpmvThreads / 32; ++w) { mn = s_min[w] < mn ? s_min[w] : mn; mx = s_max[w] > mx ? s_max[w] : mx; }
+        if (mx == 0) { mn = 0; }
+        blk_win[2 * (size_t)blockIdx.x] = (I)mn;
+        blk_win[2 * (size_t)blockIdx.x + 1] = (I)mx;
+        atomicMax(max_win, mx - mn);
+    }
+}
+
+void plan_free(SpmvPlan& p) {
+    if (p.blk_rows) cudaFree(p.blk_rows);
+    if (p.blk_win) cudaFree(p.blk_win);
+    p = SpmvPlan();
+}
+
+static int env_int(const char* name, int dflt) {
+    const char* s = getenv(name);
+    return (s && *s) ? atoi(s) : dflt;
+}
+
+static int pick_lanes(double mean_len) {
+    if (mean_len <= 1.5) return 1;
+    if (mean_len <= 3.0) return 2;
+    if (mean_len <= 6.0) return 4;
+    if (mean_len <= 12.0) return 8;
+    if (mean_len <= 24.0) return 16;
+    return 32;
+}
+
+// Staging capacity (elements) and merge target of the stream kernels.  Defaults keep 8 CTAs of 256
+// threads resident per SM with room left for L1 (x gathers): f32 18 KB, f64 24 KB of products per CTA.
+static void stream_shape(const smb200_crs* m, int variant, unsigned* cap, unsigned* target) {
+    unsigned c, t;
+    if (variant == SMB200_SPMV_STREAM) {
+        c = m->vt == SMB200_F64 ? 3072u : 4608u;
+    } else {
+        // TMA variants stage values + columns: keep the footprint comparable
+        const size_t per = vsize(m->vt) + isize(m->it);
+        c = (unsigned)((36u * 1024u) / per) & ~3u;
+    }
+    c = (unsigned)env_int("SMB200_STREAM_CAP", (int)c) & ~3u;
+    if (c < 256) c = 256;
+    t = c - c / 9;                     // leave room for the row that straddles the target
+    t = (unsigned)env_int("SMB200_STREAM_TARGET", (int)t);
+    if (t + 8 > c) t = c - 8;
+    *cap = c;
+    *target = t;
+}
+
+struct PlanShape { unsigned cap = 0, target = 0, win_cap = 0; };
+static PlanShape g_shape_of_plan(const smb200_crs* m, const SpmvPlan& p) {
+    PlanShape s;
+    if (p.variant >= SMB200_SPMV_STREAM) stream_shape(m, p.variant, &s.cap, &s.target);
+    if (p.variant == SMB200_SPMV_BANDED) {
+        const unsigned xa = (unsigned)(16 / vsize(m->vt));
+        s.win_cap = (unsigned)((p.max_win + 2 * xa) & ~(uint64_t)(xa - 1));
+    }
+    return s;
+}
+
+smb200_status plan_build_range(smb200_crs* m, SpmvPlan& p, int want_variant, int want_lanes, uint32_t flags,
+                               uint64_t rb, uint64_t re) {
+    smb200_ctx* ctx = m->ctx;
+    plan_free(p);
+    p.flags = flags;
+    const uint64_t rows = re - rb;
+    const double mean = m->n_rows ? (double)m->nnz / (double)m->n_rows : 0.0;
+    int variant = want_variant;
+    if (variant == SMB200_SPMV_AUTO) variant = env_int("SMB200_SPMV_VARIANT", SMB200_SPMV_AUTO);
+    if (variant == SMB200_SPMV_AUTO) {
+        // Row-length statistics decide: short/medium rows -> stream (balanced, bit-exact row sums);
+        // long regular rows -> a warp per row reads them with full coalescing and no staging.
+        variant = (mean >= 96.0 && m->max_row_len < 8 * (uint64_t)mean + 4096) ? SMB200_SPMV_VECTOR : SMB200_SPMV_STREAM;
+    }
+    p.variant = variant;
+    p.lanes = 0;
+    if (variant == SMB200_SPMV_SCALAR) p.lanes = 1;
+    if (variant == SMB200_SPMV_VECTOR) {
+        int l = want_lanes > 0 ? want_lanes : env_int("SMB200_SPMV_LANES", 0);
+        if (l <= 0) l = pick_lanes(mean);
+        SMB_REQUIRE(l == 1 || l == 2 || l == 4 || l == 8 || l == 16 || l == 32, SMB200_ERR_INVALID,
+                    "spmv: lanes must be a power of two in [1,32], got %d", l);
+        p.lanes = l;
+    }
+    if (variant >= SMB200_SPMV_STREAM && rows > 0) {
+        unsigned cap, target;
+        stream_shape(m, variant, &cap, &target);
+        // total merge length of the range, from the two boundary offsets
+        uint64_t ob = 0, oe = 0;
+        const size_t is = isize(m->it);
+        if (m->it == SMB200_U64) {
+            SMB_CUDA(cudaMemcpyAsync(&ob, (const char*)m->offsets + rb * is, 8, cudaMemcpyDeviceToHost, ctx->stream));
+            SMB_CUDA(cudaMemcpyAsync(&oe, (const char*)m->offsets + re * is, 8, cudaMemcpyDeviceToHost, ctx->stream));
+            SMB_CUDA(cudaStreamSynchronize(ctx->stream));
+        } else {
+            uint32_t b32 = 0, e32 = 0;
+            SMB_CUDA(cudaMemcpyAsync(&b32, (const char*)m->offsets + rb * is, 4, cudaMemcpyDeviceToHost, ctx->stream));
+            SMB_CUDA(cudaMemcpyAsync(&e32, (const char*)m->offsets + re * is, 4, cudaMemcpyDeviceToHost, ctx->stream));
+            SMB_CUDA(cudaStreamSynchronize(ctx->stream));
+            ob = b32; oe = e32;
+        }
+        const uint64_t merge_len = rows + (oe - ob);
+        p.n_blocks = (merge_len + target - 1) / target;
+        if (p.n_blocks == 0) p.n_blocks = 1;
+        SMB_REQUIRE(p.n_blocks < 0x7FFFFFFFull, SMB200_ERR_UNSUPPORTED, "spmv: too many row blocks");
+        SMB_CUDA(cudaMalloc(&p.blk_rows, (p.n_blocks + 1) * is));
+        const unsigned g = (unsigned)((p.n_blocks + 1 + 255) / 256);
+        if (m->it == SMB200_U64) split_rows_kernel<uint64_t><<<g, 256, 0, ctx->stream>>>((const uint64_t*)m->offsets, rb, re, target, p.n_blocks, (uint64_t*)p.blk_rows);
+        else split_rows_kernel<uint32_t><<<g, 256, 0, ctx->stream>>>((const uint32_t*)m->offsets, rb, re, target, p.n_blocks, (uint32_t*)p.blk_rows);
+        count_launch();
+        SMB_CUDA(cudaGetLastError());
+        if (variant == SMB200_SPMV_BANDED) {
+            SMB_CUDA(cudaMalloc(&p.blk_win, 2 * p.n_blocks * is));
+            unsigned long long* d_max = nullptr;
+            SMB_CUDA(cudaMalloc(&d_max, sizeof(unsigned long long)));
+            cudaMemsetAsync(d_max, 0, sizeof(unsigned long long), ctx->stream);
+            if (m->it == SMB200_U64) block_window_kernel<uint64_t><<<(unsigned)p.n_blocks, kSpmvThreads, 0, ctx->stream>>>((const uint64_t*)m->columns, (const uint64_t*)m->offsets, (const uint64_t*)p.blk_rows, (uint64_t*)p.blk_win, d_max);
+            else block_window_kernel<uint32_t><<<(unsigned)p.n_blocks, kSpmvThreads, 0, ctx->stream>>>((const uint32_t*)m->columns, (const uint32_t*)m->offsets, (const uint32_t*)p.blk_rows, (uint32_t*)p.blk_win, d_max);
+            count_launch();
+            unsigned long long h_max = 0;
+            cudaError_t e = cudaMemcpyAsync(&h_max, d_max, sizeof h_max, cudaMemcpyDeviceToHost, ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+            cudaFree(d_max);
+            SMB_CUDA(e);
+            p.max_win = h_max;
+            // the window must fit next to the slice in shared memory; otherwise fall back to K3-TMA
+            const size_t per = vsize(m->vt) + isize(m->it);
+            const size_t need = (size_t)cap * per + (size_t)(h_max + 8) * vsize(m->vt) + 2048;
+            if (need > 200u * 1024u) {
+                p.variant = SMB200_SPMV_STREAM_TMA;
+                cudaFree(p.blk_win);
+                p.blk_win = nullptr;
+            }
+        }
+    }
+    p.built = true;
+    return SMB200_OK;
+}
+
+smb200_status plan_build(smb200_crs* m) {
+    return plan_build_range(m, m->plan, m->want_variant, m->want_lanes, m->want_flags, 0, m->n_rows);
+}
+
+// ---- launch ---------------------------------------------------------------------------------------------
+template <class T, class I, bool DOT>
+static smb200_status launch_typed(smb200_crs* m, const SpmvPlan& p, uint64_t rb, uint64_t re, const void* x, void* y,
+                                  const DotArgs& dot) {
+    smb200_ctx* ctx = m->ctx;
+    const T* vals = (const T*)m->values;
+    const I* cols = (const I*)m->columns;
+    const I* offs = (const I*)m->offsets;
+    const T* xx = (const T*)x;
+    T* yy = (T*)y;
+    cudaStream_t st = ctx->stream;
+    if (p.variant == SMB200_SPMV_SCALAR || p.variant == SMB200_SPMV_VECTOR) {
+        const uint64_t rows = re - rb;
+        const int rows_per_cta = kSpmvThreads / p.lanes;
+        const uint64_t grid = (rows + rows_per_cta - 1) / rows_per_cta;
+        SMB_REQUIRE(grid < 0x7FFFFFFFull, SMB200_ERR_UNSUPPORTED, "spmv: grid too large");
+        switch (p.lanes) {
+#define SMB_VEC_CASE(L) case L: spmv_vector_kernel<T, I, L, DOT><<<(unsigned)grid, kSpmvThreads, 0, st>>>(vals, cols, offs, rb, re, xx, yy, dot); break;
+            SMB_VEC_CASE(1) SMB_VEC_CASE(2) SMB_VEC_CASE(4) SMB_VEC_CASE(8) SMB_VEC_CASE(16) SMB_VEC_CASE(32)
+#undef SMB_VEC_CASE
+            default: SMB_FAIL(SMB200_ERR_INVALID, "spmv: bad lane count %d", p.lanes);
+        }
+    } else {
+        const PlanShape sh = g_shape_of_plan(m, p);
+        const int carve = env_int("SMB200_CARVEOUT", -1);
+        if (p.variant == SMB200_SPMV_STREAM) {
+            const size_t smem = (size_t)(sh.cap + 8) * sizeof(T);
+            auto kern = spmv_stream_kernel<T, I, DOT>;
+            if (smem > 48 * 1024) SMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (carve >= 0) SMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+            kern<<<(unsigned)p.n_blocks, kSpmvThreads, smem, st>>>(vals, cols, offs, (const I*)p.blk_rows, sh.cap, xx, yy, dot);
+        } else if (p.variant == SMB200_SPMV_STREAM_TMA) {
+            const size_t smem = (size_t)sh.cap * (sizeof(T) + sizeof(I));
+            auto kern = spmv_stream_tma_kernel<T, I, DOT, false>;
+            if (smem > 48 * 1024) SMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (carve >= 0) SMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+            kern<<<(unsigned)p.n_blocks, kSpmvThreads, smem, st>>>(vals, cols, offs, (const I*)p.blk_rows, nullptr, sh.cap, 0u, xx, yy, dot);
+        } else {
+            const size_t smem = (size_t)sh.cap * (sizeof(T) + sizeof(I)) + (size_t)sh.win_cap * sizeof(T);
+            auto kern = spmv_stream_tma_kernel<T, I, DOT, true>;
+            if (smem > 48 * 1024) SMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (carve >= 0) SMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+            kern<<<(unsigned)p.n_blocks, kSpmvThreads, smem, st>>>(vals, cols, offs, (const I*)p.blk_rows, (const I*)p.blk_win, sh.cap, sh.win_cap, xx, yy, dot);
+        }
+    }
+    count_launch();
+    SMB_CUDA(cudaGetLastError());
+    return SMB200_OK;
+}
+
+static smb200_status set_l2_window(smb200_ctx* ctx, const void* base, size_t bytes, bool on) {
+    cudaStreamAttrValue attr;
+    memset(&attr, 0, sizeof attr);
+    if (on && ctx->l2_persist_max > 0) {
+        static thread_local int limit_set_for = -1;
+        if (limit_set_for != ctx->device) {
+            SMB_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, ctx->l2_persist_max));
+            limit_set_for = ctx->device;
+        }
+        int max_win = 0;
+        SMB_CUDA(cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device));
+        size_t win = bytes < (size_t)max_win ? bytes : (size_t)max_win;
+        attr.accessPolicyWindow.base_ptr = const_cast<void*>(base);
+        attr.accessPolicyWindow.num_bytes = win;
+        double ratio = (double)ctx->l2_persist_max / (double)(win ? win : 1);
+        attr.accessPolicyWindow.hitRatio = (float)(ratio > 1.0 ? 1.0 : ratio);
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    } else {
+        attr.accessPolicyWindow.num_bytes = 0;
+        attr.accessPolicyWindow.hitRatio = 0.f;
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyNormal;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+    }
+    SMB_CUDA(cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+    return SMB200_OK;
+}
+
+static smb200_status spmv_launch_impl(smb200_crs* m, const SpmvPlan& p, uint64_t rb, uint64_t re, const void* x, void* y,
+                                      const void* w, double* result, double* roll_dst, const double* roll_src,
+                                      const double* done) {
+    if (re <= rb) return SMB200_OK;
+    smb200_ctx* ctx = m->ctx;
+    DotArgs dot{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    if (w) {
+        uint64_t blocks = p.variant >= SMB200_SPMV_STREAM ? p.n_blocks : ((re - rb) * (uint64_t)p.lanes + kSpmvThreads - 1) / kSpmvThreads;
+        SMB_TRY(ensure_reduction_scratch(ctx, blocks));
+        dot = DotArgs{w, ctx->red_partials, ctx->red_ticket, result, roll_dst, roll_src, done};
+    }
+    static thread_local const void* window_on = nullptr;
+    if (p.flags & SMB200_FLAG_L2_PERSIST_X) {
+        if (window_on != x) { SMB_TRY(set_l2_window(ctx, x, (size_t)m->n_cols * vsize(m->vt), true)); window_on = x; }
+    } else if (window_on) {
+        SMB_TRY(set_l2_window(ctx, nullptr, 0, false));
+        window_on = nullptr;
+    }
+#define SMB_LAUNCH(T, I) (w ? launch_typed<T, I, true>(m, p, rb, re, x, y, dot) : launch_typed<T, I, false>(m, p, rb, re, x, y, dot))
+    if (m->vt == SMB200_F64) return m->it == SMB200_U64 ? SMB_LAUNCH(double, uint64_t) : SMB_LAUNCH(double, uint32_t);
+    return m->it == SMB200_U64 ? SMB_LAUNCH(float, uint64_t) : SMB_LAUNCH(float, uint32_t);
+#undef SMB_LAUNCH
+}
+
+smb200_status spmv_launch_plan(smb200_crs* m, const SpmvPlan& p, uint64_t rb, uint64_t re, const void* x, void* y,
+                               const void* w, int dot_slot) {
+    return spmv_launch_impl(m, p, rb, re, x, y, w, m->ctx->red_result + dot_slot, nullptr, nullptr, nullptr);
+}
+
+// CG kernel A: ap = A p with p.Ap fused into partial slot `slot`; S is the solver's scalar block
+// (cg.cu: S_RR=0, S_PAP=1..3, S_RR_NEW=4, S_DONE=7).  `roll` makes the launch also do rr <- rr_new.
+smb200_status spmv_launch_cg(smb200_crs* m, const SpmvPlan& p, uint64_t rb, uint64_t re, const void* x, void* y,
+                             const void* w, double* S, int slot, bool roll) {
+    return spmv_launch_impl(m, p, rb, re, x, y, w, S + 1 + slot, roll ? S + 0 : nullptr, S + 4, S + 7);
+}
+
+smb200_status spmv_launch(smb200_crs* m, const void* x, void* y, const void* w, int dot_slot, uint64_t, uint64_t) {
+    if (m->n_rows == 0) return SMB200_OK;
+    if (!m->plan.built) SMB_TRY(plan_build(m));
+    return spmv_launch_plan(m, m->plan, 0, m->n_rows, x, y, w, dot_slot);
+}
+
+}  // namespace smb
+
+using namespace smb;
+
+extern "C" {
+
+smb200_status smb200_crs_configure(smb200_crs* m, smb200_spmv_variant variant, int32_t lanes, uint32_t flags) {
+    SMB_REQUIRE(m, SMB200_ERR_INVALID, "crs_configure: NULL argument");
+    SMB_REQUIRE(variant >= SMB200_SPMV_AUTO && variant <= SMB200_SPMV_BANDED, SMB200_ERR_INVALID, "crs_configure: bad variant %d", (int)variant);
+    m->want_variant = variant;
+    m->want_lanes = lanes;
+    m->want_flags = flags;
+    cudaStreamSynchronize(m->ctx->stream);
+    plan_free(m->plan);
+    if (m->n_rows == 0) return SMB200_OK;
+    return plan_build(m);
+}
+
+smb200_status smb200_crs_plan_info(const smb200_crs* cm, smb200_plan_info* out) {
+    SMB_REQUIRE(cm && out, SMB200_ERR_INVALID, "crs_plan_info: NULL argument");
+    smb200_crs* m = const_cast<smb200_crs*>(cm);
+    if (!m->plan.built && m->n_rows) SMB_TRY(plan_build(m));
+    memset(out, 0, sizeof *out);
+    out->variant = m->plan.variant;
+    out->lanes = m->plan.lanes;
+    out->flags = m->plan.flags;
+    out->n_blocks = m->plan.n_blocks;
+    out->n_rows = m->n_rows;
+    out->n_cols = m->n_cols;
+    out->nnz = m->nnz;
+    out->max_row_len = m->max_row_len;
+    out->mean_row_len = m->n_rows ? (double)m->nnz / (double)m->n_rows : 0.0;
+    out->algorithmic_bytes = m->nnz * (vsize(m->vt) + isize(m->it)) + (m->n_rows + 1) * isize(m->it) +
+                             m->n_cols * vsize(m->vt) + m->n_rows * vsize(m->vt);
+    out->launches_per_spmv = 1;
+    return SMB200_OK;
+}
+
+smb200_status smb200_spmv(smb200_crs* a, const smb200_vec* x, smb200_vec* y) {
+    SMB_REQUIRE(a && x && y, SMB200_ERR_INVALID, "spmv: NULL argument");
+    SMB_REQUIRE(x->vt == a->vt && y->vt == a->vt, SMB200_ERR_INVALID, "spmv: value types differ");
+    SMB_REQUIRE(x->ctx == a->ctx && y->ctx == a->ctx, SMB200_ERR_INVALID, "spmv: operands belong to different contexts");
+    SMB_REQUIRE(x->d != y->d || a->n_rows == 0, SMB200_ERR_INVALID, "spmv: x and y alias");
+    // rhs.get(col) would panic for col >= x.dim (densevec.rs:40-42); n_cols = max col + 1
+    SMB_REQUIRE(x->cap >= a->n_cols && x->n + a->x_extra >= a->n_cols, SMB200_ERR_DIM,
+                "Dimension mismatch: x has %llu entries, matrix has %llu columns", (unsigned long long)x->n,
+                (unsigned long long)(a->n_cols - a->x_extra));
+    SMB_REQUIRE(y->n >= a->n_rows, SMB200_ERR_DIM, "Dimension mismatch: y has %llu entries, matrix has %llu rows",
+                (unsigned long long)y->n, (unsigned long long)a->n_rows);
+    return spmv_launch(a, x->d, y->d, nullptr, 0);
+}
+
+smb200_status smb200_spmv_host(smb200_crs* a, const void* x_host, uint64_t nx, void* y_host) {
+    SMB_REQUIRE(a && (x_host || nx == 0) && (y_host || a->n_rows == 0), SMB200_ERR_INVALID, "spmv_host: NULL argument");
+    SMB_REQUIRE(nx >= a->n_cols, SMB200_ERR_DIM, "Dimension mismatch: x has %llu entries, matrix has %llu columns",
+                (unsigned long long)nx, (unsigned long long)a->n_cols);
+    smb200_ctx* ctx = a->ctx;
+    const size_t es = vsize(a->vt);
+    const size_t xb = (size_t)a->n_cols * es, yb = (size_t)a->n_rows * es;
+    if (ctx->stage_x_bytes < xb) {
+        if (ctx->stage_x) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->stage_x); ctx->stage_x = nullptr; ctx->stage_x_bytes = 0; }
+        SMB_TRY(dev_alloc(&ctx->stage_x, xb));
+        ctx->stage_x_bytes = xb;
+    }
+    if (ctx->stage_y_bytes < yb) {
+        if (ctx->stage_y) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->stage_y); ctx->stage_y = nullptr; ctx->stage_y_bytes = 0; }
+        SMB_TRY(dev_alloc(&ctx->stage_y, yb));
+        ctx->stage_y_bytes = yb;
+    }
+    if (xb) SMB_CUDA(cudaMemcpyAsync(ctx->stage_x, x_host, xb, cudaMemcpyHostToDevice, ctx->stream));
+    SMB_TRY(spmv_launch(a, ctx->stage_x, ctx->stage_y, nullptr, 0));
+    if (yb) SMB_CUDA(cudaMemcpyAsync(y_host, ctx->stage_y, yb, cudaMemcpyDeviceToHost, ctx->stream));
+    SMB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SMB200_OK;
+}
+
+smb200_status smb200_bilinear(smb200_crs* a, const smb200_vec* lhs, const smb200_vec* rhs, double* out) {
+    SMB_REQUIRE(a && lhs && rhs && out, SMB200_ERR_INVALID, "bilinear: NULL argument");
+    SMB_REQUIRE(lhs->vt == a->vt && rhs->vt == a->vt, SMB200_ERR_INVALID, "bilinear: value types differ");
+    SMB_REQUIRE(rhs->cap >= a->n_cols && rhs->n + a->x_extra >= a->n_cols, SMB200_ERR_DIM, "Dimension mismatch");
+    SMB_REQUIRE(lhs->n >= a->n_rows, SMB200_ERR_DIM, "Dimension mismatch");
+    if (a->n_rows == 0) { *out = 0.0; return SMB200_OK; }
+    smb200_ctx* ctx = a->ctx;
+    const size_t yb = (size_t)a->n_rows * vsize(a->vt);
+    if (ctx->stage_y_bytes < yb) {
+        if (ctx->stage_y) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->stage_y); ctx->stage_y = nullptr; ctx->stage_y_bytes = 0; }
+        SMB_TRY(dev_alloc(&ctx->stage_y, yb));
+        ctx->stage_y_bytes = yb;
+    }
+    SMB_TRY(spmv_launch(a, rhs->d, ctx->stage_y, lhs->d, 1));
+    return fetch_result(ctx, 1, out);
+}
+
+}  // extern "C"
