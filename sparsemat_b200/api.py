@@ -96,10 +96,9 @@ def pinned_empty(n: int, dtype) -> np.ndarray:
     dt = np.dtype(dtype)
     p = C.c_void_p()
     check(lib.smb200_host_alloc(max(1, n * dt.itemsize), C.byref(p)))
-    buf = (C.c_char * (n * dt.itemsize)).from_address(p.value)
-    arr = np.frombuffer(buf, dtype=dt, count=n)
-    arr._smb_pinned = _PinnedOwner(p)  # keep alive with the array
-    return arr
+    buf = (C.c_char * max(1, n * dt.itemsize)).from_address(p.value)
+    buf._smb_pinned = _PinnedOwner(p)  # the array keeps `buf` alive, `buf` keeps the allocation alive
+    return np.frombuffer(buf, dtype=dt, count=n)
 
 
 class _PinnedOwner:

@@ -79,6 +79,11 @@ struct smb200_ctx {
     // NCCL (dist.cu); opaque here
     void* comm = nullptr;
     int rank = 0, world = 1;
+    // lifetime: every vector / matrix / event / dist handle created from the context holds a reference; a
+    // smb200_ctx_destroy issued while handles are still alive is deferred until the last one is freed
+    // (garbage-collected language bindings finalise objects in arbitrary order).
+    int refs = 0;
+    bool destroy_requested = false;
 };
 
 struct smb200_vec {
@@ -146,6 +151,8 @@ struct smb200_crs {
 namespace smb {
 
 // implemented across the .cu files
+void ctx_retain(smb200_ctx* ctx);
+void ctx_release(smb200_ctx* ctx);   // may tear the context down if its destruction was deferred
 smb200_status dev_alloc(void** p, size_t bytes);
 smb200_status crs_alloc(smb200_ctx* ctx, int vt, int it, uint64_t n_rows, uint64_t n_cols, uint64_t nnz,
                         smb200_crs** out);

@@ -14,6 +14,13 @@ void set_error(const char* fmt, ...) {
 }
 const char* get_error() { return g_err; }
 
+void ctx_teardown(smb200_ctx* c);
+void ctx_retain(smb200_ctx* ctx) { if (ctx) ++ctx->refs; }
+void ctx_release(smb200_ctx* ctx) {
+    if (!ctx) return;
+    if (--ctx->refs <= 0 && ctx->destroy_requested) ctx_teardown(ctx);
+}
+
 smb200_status dev_alloc(void** p, size_t bytes) {
     *p = nullptr;
     SMB_CUDA(cudaMalloc(p, bytes + kPadBytes));
@@ -100,6 +107,19 @@ smb200_status smb200_comm_destroy(smb200_ctx* ctx);
 
 smb200_status smb200_ctx_destroy(smb200_ctx* c) {
     if (!c) return SMB200_OK;
+    if (c->refs > 0) {                 // handles still alive: finish when the last one is freed
+        c->destroy_requested = true;
+        if (c->stream) cudaStreamSynchronize(c->stream);
+        return SMB200_OK;
+    }
+    ctx_teardown(c);
+    return SMB200_OK;
+}
+
+}  // extern "C"
+
+namespace smb {
+void ctx_teardown(smb200_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->comm) smb200_comm_destroy(c);
@@ -115,8 +135,10 @@ smb200_status smb200_ctx_destroy(smb200_ctx* c) {
     if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
-    return SMB200_OK;
 }
+}  // namespace smb
+
+extern "C" {
 
 smb200_status smb200_ctx_sync(smb200_ctx* ctx) {
     SMB_REQUIRE(ctx, SMB200_ERR_INVALID, "ctx_sync: NULL context");
@@ -158,6 +180,7 @@ smb200_status smb200_event_create(smb200_ctx* ctx, smb200_event** out) {
     e->ctx = ctx;
     cudaError_t err = cudaEventCreate(&e->ev);
     if (err != cudaSuccess) { delete e; SMB_CUDA(err); }
+    ctx_retain(ctx);
     *out = e;
     return SMB200_OK;
 }
@@ -175,7 +198,9 @@ smb200_status smb200_event_elapsed_ms(smb200_event* start, smb200_event* stop, f
 smb200_status smb200_event_destroy(smb200_event* ev) {
     if (!ev) return SMB200_OK;
     cudaEventDestroy(ev->ev);
+    smb200_ctx* ctx = ev->ctx;
     delete ev;
+    ctx_release(ctx);
     return SMB200_OK;
 }
 

@@ -162,6 +162,7 @@ smb200_status crs_alloc(smb200_ctx* ctx, int vt, int it, uint64_t n_rows, uint64
     SMB_CUDA(cudaSetDevice(ctx->device));
     smb200_crs* m = new smb200_crs();
     m->ctx = ctx; m->vt = vt; m->it = it; m->n_rows = n_rows; m->n_cols = n_cols; m->nnz = nnz;
+    ctx_retain(ctx);
     smb200_status s = SMB200_OK;
     if (nnz) {
         s = dev_alloc(&m->values, nnz * vsize(vt));
@@ -354,7 +355,9 @@ smb200_status smb200_crs_free(smb200_crs* m) {
     if (m->values) cudaFree(m->values);
     if (m->columns) cudaFree(m->columns);
     if (m->offsets) cudaFree(m->offsets);
+    smb200_ctx* ctx = m->ctx;
     delete m;
+    ctx_release(ctx);
     return SMB200_OK;
 }
 

@@ -294,7 +294,9 @@ smb200_status smb200_dist_free(smb200_dist* d) {
     if (d->send_idx) cudaFree(d->send_idx);
     if (d->send_buf) cudaFree(d->send_buf);
     if (d->local) smb200_crs_free(d->local);
+    smb200_ctx* ctx = d->ctx;
     delete d;
+    ctx_release(ctx);
     return SMB200_OK;
 }
 
@@ -308,6 +310,7 @@ smb200_status smb200_dist_create(smb200_ctx* ctx, smb200_vtype vt, smb200_itype 
     *out = nullptr;
     smb200_dist* d = new smb200_dist();
     d->ctx = ctx; d->vt = vt; d->it = it; d->n_global = n_global;
+    ctx_retain(ctx);
     d->bounds.assign(bounds, bounds + world + 1);
     d->row_lo = bounds[me];
     d->n_local = bounds[me + 1] - bounds[me];
@@ -319,11 +322,11 @@ smb200_status smb200_dist_create(smb200_ctx* ctx, smb200_vtype vt, smb200_itype 
     std::vector<unsigned char> cols_local(nnz_local * isize(it));
     if (s == SMB200_OK)
         s = smb200_ghost_plan(it, nnz_local, columns_global, (uint32_t)world, (uint32_t)me, bounds, cols_local.data(), ghosts.data(), &n_ghost, d->recv_count.data());
-    if (s != SMB200_OK) { delete d; return s; }
+    if (s != SMB200_OK) { smb200_dist_free(d); return s; }
     d->n_ghost = n_ghost;
     d->recv_count[me] = 0;
     s = smb200_crs_upload(ctx, vt, it, d->n_local, d->n_local + n_ghost, nnz_local, values, cols_local.data(), offset_rows_local, &d->local);
-    if (s != SMB200_OK) { delete d; return s; }
+    if (s != SMB200_OK) { smb200_dist_free(d); return s; }
     d->local->x_extra = n_ghost;
     // interior = longest run of rows without ghost references
     {
@@ -356,6 +359,7 @@ smb200_status smb200_dist_laplace(smb200_ctx* ctx, smb200_vtype vt, smb200_itype
     *out = nullptr;
     smb200_dist* d = new smb200_dist();
     d->ctx = ctx; d->vt = vt; d->it = it; d->n_global = N;
+    ctx_retain(ctx);
     d->bounds.resize(world + 1);
     // whole z-planes per rank, as even as possible
     for (int q = 0; q <= world; ++q) d->bounds[q] = (nz * (uint64_t)q / (uint64_t)world) * plane;
@@ -364,7 +368,7 @@ smb200_status smb200_dist_laplace(smb200_ctx* ctx, smb200_vtype vt, smb200_itype
     const uint64_t n_lo = (nz > 1 && me > 0) ? plane : 0, n_hi = (nz > 1 && me + 1 < world) ? plane : 0;
     d->n_ghost = n_lo + n_hi;
     smb200_status s = gen_laplace_block(ctx, vt, it, nx, ny, nz, d->row_lo, d->row_lo + d->n_local, 1, n_lo, d->n_local + d->n_ghost, &d->local);
-    if (s != SMB200_OK) { delete d; return s; }
+    if (s != SMB200_OK) { smb200_dist_free(d); return s; }
     d->local->x_extra = d->n_ghost;
     d->recv_count.assign(world, 0);
     d->recv_off.assign(world, 0);

@@ -171,6 +171,7 @@ static smb200_status vec_make(smb200_ctx* ctx, smb200_vtype vt, uint64_t n, uint
     if (s != SMB200_OK) { delete v; return s; }
     cudaError_t e = cudaMemsetAsync(v->d, 0, v->cap * vsize(vt) + kPadBytes, ctx->stream);
     if (e != cudaSuccess) { cudaFree(v->d); delete v; SMB_CUDA(e); }
+    ctx_retain(ctx);
     *out = v;
     return SMB200_OK;
 }
@@ -193,6 +194,7 @@ smb200_status smb200_vec_wrap(smb200_ctx* ctx, smb200_vtype vt, uint64_t n, void
     SMB_REQUIRE(((uintptr_t)device_ptr % vsize(vt)) == 0, SMB200_ERR_INVALID, "vec_wrap: pointer not element aligned");
     smb200_vec* v = new smb200_vec();
     v->ctx = ctx; v->vt = vt; v->n = n; v->cap = n; v->d = device_ptr; v->owned = false;
+    ctx_retain(ctx);
     *out = v;
     return SMB200_OK;
 }
@@ -204,7 +206,9 @@ smb200_status smb200_vec_free(smb200_vec* v) {
         cudaStreamSynchronize(v->ctx->stream);
         cudaFree(v->d);
     }
+    smb200_ctx* ctx = v->ctx;
     delete v;
+    ctx_release(ctx);
     return SMB200_OK;
 }
 

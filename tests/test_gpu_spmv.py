@@ -1,0 +1,165 @@
+"""GPU parity of the hot path: SparseMatrix::mvp over SparseMatCRS (sparsematrix.rs:146-158,
+sparsemat_crs.rs:102-110) — libsmb200's SpMV kernels against the oracle on identical inputs.
+
+Bar (BASELINE.json north_star): bit-exact wherever a row is summed in storage order (scalar kernel; the
+stream kernels for rows of <= 64 entries), otherwise |got - want| <= tol * (|A||x|)_i with tol = 1e-5 (f32) /
+1e-12 (f64)."""
+import numpy as np
+import pytest
+
+import cases
+
+pytestmark = pytest.mark.gpu
+
+F32, F64, U32, U64 = np.float32, np.float64, np.uint32, np.uint64
+COMBOS = [(F32, U32), (F64, U32), (F32, U64), (F64, U64)]
+
+
+def _variants(smb):
+    return [(smb.SPMV_SCALAR, 0), (smb.SPMV_VECTOR, 2), (smb.SPMV_VECTOR, 4), (smb.SPMV_VECTOR, 8), (smb.SPMV_VECTOR, 16),
+            (smb.SPMV_VECTOR, 32), (smb.SPMV_STREAM, 0), (smb.SPMV_STREAM_TMA, 0), (smb.SPMV_BANDED, 0), (smb.SPMV_AUTO, 0)]
+
+
+def _check(smb, orc, ctx, case, seed=11, x_extra=0):
+    n_rows, n_cols, vals, cols, offs = case
+    x = np.random.default_rng(seed).uniform(-1, 1, n_cols + x_extra).astype(vals.dtype)
+    want = orc.mvp(vals, cols, offs, x)
+    scale = cases.abs_rowsum(vals, cols, offs, x) + np.finfo(np.float64).tiny
+    tol = cases.TOL[vals.dtype]
+    max_len = int(np.max(np.diff(offs.astype(np.int64)))) if n_rows else 0
+    a = smb.SparseMatCRS.from_raw_parts(ctx, n_rows, n_cols, vals, cols, offs)
+    assert (a.n_rows(), a.n_cols(), a.n_non_zero_entries()) == (n_rows, n_cols, vals.size)
+    xd = smb.DenseVec.from_vec(ctx, x)
+    for variant, lanes in _variants(smb):
+        a.configure(variant, lanes)
+        info = a.plan_info()
+        y = a.mvp(xd)
+        assert y.dim() == n_rows                       # mvp returns a vector of dim n_rows (sparsematrix.rs:148-155)
+        got = y.to_numpy()
+        name = f"{info['variant_name']}/{lanes} {vals.dtype}/{cols.dtype} rows={n_rows} nnz={vals.size}"
+        exact = variant == smb.SPMV_SCALAR or (info["variant"] >= smb.SPMV_STREAM and max_len <= 64)
+        if exact:
+            assert np.array_equal(got, want), f"{name}: not bit-exact ({np.count_nonzero(got != want)} rows differ)"
+        else:
+            err = np.abs(got.astype(np.float64) - want.astype(np.float64)) / scale
+            assert np.all(np.isfinite(got)) and float(err.max(initial=0.0)) <= tol, f"{name}: rel err {err.max():.3e}"
+        # the end-to-end entry point (host buffers) gives the same bits as the device-resident call
+        if variant in (smb.SPMV_AUTO, smb.SPMV_STREAM):
+            assert np.array_equal(a.mvp_host(x), got), name + " (host path)"
+
+
+@pytest.mark.parametrize("vdt,idt", COMBOS)
+def test_laplace_2d_and_3d_generated_on_device(smb, orc, ctx, vdt, idt):
+    """The bench workloads at toy size: device generator == oracle generator bit for bit, then SpMV."""
+    for nx, ny, nz in [(33, 17, 1), (20, 12, 9), (1, 1, 1), (5, 1, 1), (2, 2, 2)]:
+        a = smb.SparseMatCRS.laplace(ctx, vdt, idt, nx, ny, nz)
+        vals, cols, offs = orc.laplace(vdt, idt, nx, ny, nz)
+        gv, gc, go = a.raw_parts()
+        assert np.array_equal(gv, vals) and np.array_equal(gc, cols) and np.array_equal(go, offs)
+        _check(smb, orc, ctx, (nx * ny * nz, nx * ny * nz, vals, cols, offs))
+
+
+@pytest.mark.parametrize("vdt,idt", COMBOS)
+def test_ragged_rows_with_empty_rows(smb, orc, ctx, vdt, idt):
+    _check(smb, orc, ctx, cases.ragged(1, 3000, 2500, 40, vdt, idt))
+    _check(smb, orc, ctx, cases.ragged(2, 257, 4096, 130, vdt, idt))      # rows past the 64-entry storage-order limit
+
+
+@pytest.mark.parametrize("vdt,idt", COMBOS)
+def test_power_law_rows(smb, orc, ctx, vdt, idt):
+    _check(smb, orc, ctx, cases.powerlaw(3, 20000, 20000, 6000, vdt, idt))
+
+
+@pytest.mark.parametrize("vdt,idt", [(F32, U32), (F64, U64)])
+def test_one_giant_row_among_short_ones(smb, orc, ctx, vdt, idt):
+    for where in (0, None, 1499):
+        _check(smb, orc, ctx, cases.giant_row(4, 1500, 50000, 120_000, vdt, idt, where=where))
+
+
+@pytest.mark.parametrize("vdt,idt", [(F32, U32), (F64, U32)])
+def test_banded_matrix_uses_the_shared_memory_x_window(smb, orc, ctx, vdt, idt):
+    case = cases.banded(5, 40000, 600, 9, vdt, idt)
+    a = smb.SparseMatCRS.from_raw_parts(ctx, *case)
+    a.configure(smb.SPMV_BANDED)
+    assert a.plan_info()["variant"] == smb.SPMV_BANDED
+    _check(smb, orc, ctx, case)
+
+
+@pytest.mark.parametrize("vdt,idt", [(F32, U32), (F64, U64)])
+def test_edge_shapes(smb, orc, ctx, vdt, idt):
+    _check(smb, orc, ctx, cases.all_empty(7, 3, vdt, idt))                 # rows without entries: y = 0
+    _check(smb, orc, ctx, cases.ragged(6, 1, 10, 10, vdt, idt, empty_frac=0.0))
+    _check(smb, orc, ctx, cases.ragged(7, 50, 1, 5, vdt, idt))             # a single column
+    _check(smb, orc, ctx, cases.ragged(8, 300, 200, 12, vdt, idt), x_extra=17)   # x longer than n_cols is fine
+    # 0 x 0 matrix (SparseMatCRS::new()): mvp gives the empty vector
+    a = smb.SparseMatCRS.from_raw_parts(ctx, 0, 0, np.zeros(0, vdt), np.zeros(0, idt), np.zeros(0, idt))
+    assert a.mvp(smb.DenseVec(ctx, 0, vdt)).dim() == 0
+
+
+def test_reference_known_answers(smb, ctx):
+    """lib.rs:80-82 (34.544, storage order [col1, col2, col0]) and lib.rs:150-152 (20.16), f32, assert_eq!."""
+    a = smb.SparseMatCRS.from_raw_parts(ctx, 3, 3, np.array([4.2, 0.12, 7.12, 4.12, 2.24, 2.12], F32),
+                                        np.array([1, 2, 0, 2, 1, 2], U32), np.array([0, 3, 5, 6], U32))
+    v = smb.DenseVec.from_vec(ctx, np.array([2.0, 4.8, 1.2], F32))
+    for variant in (smb.SPMV_AUTO, smb.SPMV_SCALAR, smb.SPMV_STREAM, smb.SPMV_STREAM_TMA, smb.SPMV_BANDED):
+        a.configure(variant)
+        assert (a * v).get(0) == F32(34.544)
+    assert a.density() == 6.0 / 9.0                                        # lib.rs:83
+    b = smb.SparseMatCRS.from_raw_parts(ctx, 4, 4, np.array([4.2, 4.12, 2.12, 5.12, 1.12], F32),
+                                        np.array([1, 2, 2, 3, 2], U32), np.array([0, 1, 2, 3, 5], U32))
+    w = smb.DenseVec.from_vec(ctx, np.array([2.0, 4.8, 1.2, 3.4], F32))
+    assert (b * w).get(0) == F32(20.16)
+    assert b.density() == 5.0 / 16.0                                       # lib.rs:153
+    assert b.iter_row(5) == []                                             # lib.rs:148-149: past the end -> empty
+
+
+def test_dimension_mismatch_panics_like_the_reference(smb, ctx):
+    a = smb.SparseMatCRS.laplace(ctx, F64, U32, 8, 8, 1)
+    with pytest.raises(smb.Panic):                                         # rhs.get(col) out of bounds (densevec.rs:40-42)
+        a.mvp(smb.DenseVec(ctx, 63, F64))
+    with pytest.raises(smb.SmbError):                                      # malformed CRS never reaches a kernel
+        smb.SparseMatCRS.from_raw_parts(ctx, 2, 2, np.ones(2), np.array([0, 2], U32), np.array([0, 1, 2], U32))
+    with pytest.raises(smb.SmbError):
+        smb.SparseMatCRS.from_raw_parts(ctx, 2, 2, np.ones(2), np.array([0, 1], U32), np.array([0, 2, 1], U32))
+
+
+def test_bilinear_form(smb, orc, ctx):
+    """SparseMatrix::inner_prod (sparsematrix.rs:161-171): lhs^T A rhs."""
+    n_rows, n_cols, vals, cols, offs = cases.ragged(9, 5000, 4000, 20, F64, U32)
+    rng = np.random.default_rng(10)
+    lhs, rhs = rng.uniform(-1, 1, n_rows), rng.uniform(-1, 1, n_cols)
+    want = orc.bilinear(n_rows, n_cols, vals, cols, offs, lhs, rhs)
+    a = smb.SparseMatCRS.from_raw_parts(ctx, n_rows, n_cols, vals, cols, offs)
+    got = a.inner_prod(smb.DenseVec.from_vec(ctx, lhs), smb.DenseVec.from_vec(ctx, rhs))
+    scale = float(np.sum(np.abs(lhs) * cases.abs_rowsum(vals, cols, offs, rhs)))
+    assert abs(float(got) - float(want)) <= 1e-12 * scale
+
+
+def test_full_size_headline_workload_properties(smb, ctx):
+    """C2 at full size (256^3, f32/u32, 117M nnz): size-independent checks.
+    A * ones is known in closed form: 6 - (number of in-grid neighbours), exactly representable in f32;
+    linearity A(2x) == 2*A(x) bit for bit (scaling by 2 is exact); every kernel family agrees bit for bit
+    (all rows have <= 7 entries, summed in storage order)."""
+    n = 256
+    a = smb.SparseMatCRS.laplace(ctx, F32, U32, n, n, n)
+    assert a.n_non_zero_entries() == 117_047_296 and a.n_rows() == n ** 3
+    ones = smb.DenseVec(ctx, n ** 3, F32)
+    ones.fill(1.0)
+    y = a.mvp(ones).to_numpy().reshape(n, n, n)
+    idx = np.arange(n)
+    edge = ((idx == 0).astype(np.float32) + (idx == n - 1).astype(np.float32))
+    want = edge[:, None, None] + edge[None, :, None] + edge[None, None, :]
+    assert np.array_equal(y, want)
+    x = smb.DenseVec(ctx, n ** 3, F32)
+    x.fill_uniform(2)
+    ref = None
+    for variant in (smb.SPMV_STREAM, smb.SPMV_STREAM_TMA, smb.SPMV_SCALAR, smb.SPMV_AUTO):
+        a.configure(variant)
+        got = a.mvp(x).to_numpy()
+        if ref is None:
+            ref = got
+        else:
+            assert np.array_equal(got, ref), smb.VARIANT_NAMES[variant]
+    x2 = x.clone()
+    x2.scale(2.0)
+    assert np.array_equal(a.mvp(x2).to_numpy(), 2.0 * ref)
