@@ -56,7 +56,10 @@ typedef enum {
     SMB200_SPMV_STREAM = 3,  /* K3: nnz+row balanced CTAs, products staged in shared memory,
                                 storage-order per-row sums (bit-exact for rows <= 64 nnz)            */
     SMB200_SPMV_STREAM_TMA = 4, /* K3 with values/columns brought in by cp.async.bulk (TMA)          */
-    SMB200_SPMV_BANDED = 5   /* K4: STREAM_TMA + the x window of the block staged in shared memory   */
+    SMB200_SPMV_BANDED = 5,  /* K4: STREAM_TMA + the x window of the block staged in shared memory   */
+    SMB200_SPMV_STREAM_PIPE = 6 /* K3 persistent: one CTA per SM slot walks its row blocks through a
+                                multi-stage shared-memory ring filled by cp.async.bulk (TMA) + mbarrier,
+                                so the HBM stream never waits for the gather / row-sum phases         */
 } smb200_spmv_variant;
 
 /* flags for smb200_crs_configure */

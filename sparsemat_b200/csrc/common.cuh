@@ -109,6 +109,9 @@ struct SpmvPlan {
     uint32_t flags = 0;
     uint64_t n_blocks = 0;              // STREAM*: CTAs
     void* blk_rows = nullptr;           // STREAM*: [n_blocks+1] row split points, index type
+    void* blk_nnz = nullptr;            // STREAM*: [n_blocks+1] offset_rows[blk_rows[k]], index type
+    unsigned char* blk_flags = nullptr; // PIPE: per block, kBlkNoFit | kBlkLong
+    unsigned cap = 0, target = 0;       // STREAM*: staging capacity / merge target the plan was cut for (elements)
     void* blk_win = nullptr;            // BANDED: [2*n_blocks] (cmin, cmax+1) per block, index type
     uint64_t max_win = 0;               // BANDED: widest window (elements)
     bool built = false;

@@ -33,7 +33,11 @@ namespace smb {
 constexpr int kSpmvThreads = 256;
 constexpr int kWarpRowMin = 64;      // rows longer than this are reduced by a warp inside the stream kernels
 constexpr int kBigRow = 1024;        // fallback path: rows at least this long are reduced by the whole CTA
-constexpr int kLongCap = 96;         // per-CTA list of rows deferred to the warp / CTA pass
+constexpr int kLongCap = 192;        // per-CTA list of rows deferred to the warp / CTA pass (cap / 65 at most)
+constexpr unsigned kMaxCap = 12288;  // staging capacity limit implied by kLongCap
+constexpr unsigned kBlkNoFit = 1u;   // PIPE block flags: slice larger than a stage -> direct path
+constexpr unsigned kBlkLong = 2u;    //                   a row of more than kWarpRowMin entries -> two-pass row sums
+constexpr int kPipeMaxStages = 8;
 
 struct DotArgs {
     const void* w;            // weights (nullptr = no fused dot)
@@ -53,12 +57,12 @@ template <class T> __device__ __forceinline__ T warp_sum_t(T v) {
     return v;
 }
 
-template <class T>
+template <class T, int THREADS = kSpmvThreads>
 __device__ __forceinline__ void finish_dot(double acc, const DotArgs& d) {
-    __shared__ double scratch[kSpmvThreads / 32 + 1];
-    const double bsum = block_sum<kSpmvThreads>(acc, scratch);
+    __shared__ double scratch[THREADS / 32 + 1];
+    const double bsum = block_sum<THREADS>(acc, scratch);
     double total;
-    if (grid_sum<kSpmvThreads>(bsum, d.partials, d.ticket, scratch, total))
+    if (grid_sum<THREADS>(bsum, d.partials, d.ticket, scratch, total))
         if (threadIdx.x == 0) {
             *d.result = (double)(T)total;
             if (d.roll_dst) *d.roll_dst = *d.roll_src;
@@ -134,12 +138,12 @@ template <class E> __device__ __forceinline__ void store_quad_shared(E* p, const
 
 // Row sums out of the staged products.  prod[k] holds the product of element a0 + k.
 // Pass 1: one thread per row, storage order (bit-exact).  Pass 2: rows longer than kWarpRowMin, a warp each.
-template <class T, class I, bool DOT>
+template <class T, class I, bool DOT, int THREADS = kSpmvThreads>
 __device__ __forceinline__ double reduce_rows_from_smem(const T* prod, const I* __restrict__ offs, uint64_t r0, uint64_t r1,
                                                         uint64_t a0, T* __restrict__ y, const T* __restrict__ w,
                                                         unsigned int* s_long_count, unsigned int* s_long_rows) {
     double acc = 0.0;
-    for (uint64_t r = r0 + threadIdx.x; r < r1; r += kSpmvThreads) {
+    for (uint64_t r = r0 + threadIdx.x; r < r1; r += THREADS) {
         const unsigned a = (unsigned)((uint64_t)__ldg(offs + r) - a0);
         const unsigned e = (unsigned)((uint64_t)__ldg(offs + r + 1) - a0);
         if (e - a <= (unsigned)kWarpRowMin) {
@@ -155,7 +159,7 @@ __device__ __forceinline__ double reduce_rows_from_smem(const T* prod, const I* 
     __syncthreads();
     const unsigned n_long = *s_long_count;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (unsigned j = warp; j < n_long; j += kSpmvThreads / 32) {
+    for (unsigned j = warp; j < n_long; j += THREADS / 32) {
         const uint64_t r = r0 + s_long_rows[j];
         const unsigned a = (unsigned)((uint64_t)__ldg(offs + r) - a0);
         const unsigned e = (unsigned)((uint64_t)__ldg(offs + r + 1) - a0);
@@ -172,14 +176,14 @@ __device__ __forceinline__ double reduce_rows_from_smem(const T* prod, const I* 
 
 // Blocks whose slice does not fit the staging buffer (they contain a very long row): classic
 // CSR-vector inside the CTA — a warp per row, the whole CTA for rows >= kBigRow.
-template <class T, class I, bool DOT>
+template <class T, class I, bool DOT, int THREADS = kSpmvThreads>
 __device__ __forceinline__ double rows_direct(const T* __restrict__ vals, const I* __restrict__ cols, const I* __restrict__ offs,
                                               uint64_t r0, uint64_t r1, const T* __restrict__ x, T* __restrict__ y,
                                               const T* __restrict__ w, unsigned int* s_long_count, unsigned int* s_long_rows,
                                               double* scratch) {
     double acc = 0.0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (uint64_t r = r0 + warp; r < r1; r += kSpmvThreads / 32) {
+    for (uint64_t r = r0 + warp; r < r1; r += THREADS / 32) {
         const uint64_t a = (uint64_t)__ldg(offs + r), e = (uint64_t)__ldg(offs + r + 1);
         if (e - a >= (uint64_t)kBigRow) {
             if (lane == 0) {
@@ -203,14 +207,14 @@ __device__ __forceinline__ double rows_direct(const T* __restrict__ vals, const 
         const uint64_t a = (uint64_t)__ldg(offs + r), e = (uint64_t)__ldg(offs + r + 1);
         T s0 = T(0), s1 = T(0);
         uint64_t k = a + threadIdx.x;
-        for (; k + kSpmvThreads < e; k += 2 * kSpmvThreads) {
+        for (; k + THREADS < e; k += 2 * THREADS) {
             const T p0 = mul_rn(__ldg(x + (size_t)__ldcs(cols + k)), __ldcs(vals + k));
-            const T p1 = mul_rn(__ldg(x + (size_t)__ldcs(cols + k + kSpmvThreads)), __ldcs(vals + k + kSpmvThreads));
+            const T p1 = mul_rn(__ldg(x + (size_t)__ldcs(cols + k + THREADS)), __ldcs(vals + k + THREADS));
             s0 = add_rn(s0, p0);
             s1 = add_rn(s1, p1);
         }
         if (k < e) s0 = add_rn(s0, mul_rn(__ldg(x + (size_t)__ldcs(cols + k)), __ldcs(vals + k)));
-        const double tot = block_sum<kSpmvThreads>((double)s0 + (double)s1, scratch);
+        const double tot = block_sum<THREADS>((double)s0 + (double)s1, scratch);
         if (threadIdx.x == 0) {
             const T s = (T)tot;
             y[r] = s;
@@ -376,14 +380,201 @@ spmv_stream_tma_kernel(const T* __restrict__ vals, const I* __restrict__ cols, c
     if constexpr (DOT) finish_dot<T>(acc, dot);
 }
 
+// ---- K3 persistent: multi-stage TMA ring ---------------------------------------------------------------
+// One CTA per SM slot walks the row blocks b = blockIdx.x, blockIdx.x + gridDim.x, ... .  Thread 0 keeps
+// `stages - 1` blocks of values + columns in flight with cp.async.bulk into a shared-memory ring (one
+// mbarrier per stage); all threads then multiply the landed slice by the gathered x in place and sum the
+// rows in storage order.  One __syncthreads per block: the stage consumed in iteration i - 1 is refilled
+// right after the barrier of iteration i, when every thread is known to have left it.
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <class E, int G> struct Grp { E e[G]; };
+template <class E, int G> __device__ __forceinline__ Grp<E, G> lds_grp(const E* p) {
+    static_assert(sizeof(E) * G == 16 || sizeof(E) * G == 8, "group must be 8 or 16 bytes");
+    Grp<E, G> q;
+    if constexpr (sizeof(E) * G == 16) { const uint4 v = *reinterpret_cast<const uint4*>(p); memcpy(q.e, &v, 16); }
+    else { const uint2 v = *reinterpret_cast<const uint2*>(p); memcpy(q.e, &v, 8); }
+    return q;
+}
+template <class E, int G> __device__ __forceinline__ void sts_grp(E* p, const Grp<E, G>& q) {
+    if constexpr (sizeof(E) * G == 16) { uint4 v; memcpy(&v, q.e, 16); *reinterpret_cast<uint4*>(p) = v; }
+    else { uint2 v; memcpy(&v, q.e, 8); *reinterpret_cast<uint2*>(p) = v; }
+}
+
+template <class T, class I, int THREADS, bool DOT>
+__global__ void __launch_bounds__(THREADS)
+spmv_pipe_kernel(const T* __restrict__ vals, const I* __restrict__ cols, const I* __restrict__ offs,
+                 const I* __restrict__ blk_rows, const I* __restrict__ blk_nnz, const unsigned char* __restrict__ blk_flags,
+                 unsigned n_blocks, unsigned cap, unsigned stages, const T* __restrict__ x, T* __restrict__ y, DotArgs dot) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t full[kPipeMaxStages];
+    __shared__ unsigned long long s_desc[kPipeMaxStages][4];    // r0, r1, n0, n1 of the block staged there
+    __shared__ unsigned int s_flags[kPipeMaxStages];
+    __shared__ unsigned int s_long_count;
+    __shared__ unsigned int s_long_rows[kLongCap];
+    __shared__ double scratch[THREADS / 32 + 1];
+    constexpr int G = 16 / (sizeof(T) > sizeof(I) ? sizeof(T) : sizeof(I));   // elements per 16-byte group
+    constexpr int U = 4;                                                        // groups in flight per thread
+    constexpr int K = 3;                                                        // rows per thread with prefetched offsets
+    if constexpr (DOT) { if (solver_done(dot)) return; }
+    const unsigned tid = threadIdx.x;
+    const unsigned n_my = blockIdx.x < n_blocks ? (n_blocks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const size_t stage_bytes = (size_t)cap * (sizeof(T) + sizeof(I));
+    if (tid == 0) {
+        for (unsigned s = 0; s < stages; ++s) mbar_init(&full[s], 1);
+        s_long_count = 0;
+    }
+    __syncthreads();
+
+    // thread 0: publish the descriptor of block j in its stage and start the bulk copies
+    auto issue = [&](unsigned s, unsigned long long r0, unsigned long long r1, unsigned long long n0, unsigned long long n1,
+                     unsigned fl) {
+        s_desc[s][0] = r0; s_desc[s][1] = r1; s_desc[s][2] = n0; s_desc[s][3] = n1;
+        s_flags[s] = fl;
+        const unsigned long long a0 = n0 & ~3ull;
+        const unsigned count = (fl & kBlkNoFit) ? 0u : (unsigned)(((n1 - a0) + 3ull) & ~3ull);
+        if (count == 0) { mbar_arrive(&full[s]); return; }
+        unsigned char* base = smem_raw + (size_t)s * stage_bytes;
+        mbar_expect_tx(&full[s], count * (unsigned)(sizeof(T) + sizeof(I)));
+        bulk_g2s(base, vals + a0, count * (unsigned)sizeof(T), &full[s]);
+        bulk_g2s(base + (size_t)cap * sizeof(T), cols + a0, count * (unsigned)sizeof(I), &full[s]);
+    };
+    auto blk = [&](unsigned j) { return (size_t)blockIdx.x + (size_t)j * gridDim.x; };
+
+    // prologue: stages - 1 blocks in flight; the descriptors are fetched by the first lanes in parallel
+    const unsigned pro = n_my < stages - 1 ? n_my : stages - 1;
+    if (tid < 32) {
+        unsigned long long r0 = 0, r1 = 0, n0 = 0, n1 = 0;
+        unsigned fl = 0;
+        if (tid < pro) {
+            const size_t b = blk(tid);
+            r0 = (unsigned long long)__ldg(blk_rows + b); r1 = (unsigned long long)__ldg(blk_rows + b + 1);
+            n0 = (unsigned long long)__ldg(blk_nnz + b); n1 = (unsigned long long)__ldg(blk_nnz + b + 1);
+            fl = __ldg(blk_flags + b);
+        }
+        for (unsigned j = 0; j < pro; ++j) {
+            const unsigned long long a = __shfl_sync(0xffffffffu, r0, j), b2 = __shfl_sync(0xffffffffu, r1, j);
+            const unsigned long long c = __shfl_sync(0xffffffffu, n0, j), d = __shfl_sync(0xffffffffu, n1, j);
+            const unsigned f = __shfl_sync(0xffffffffu, fl, j);
+            if (tid == 0) issue(j, a, b2, c, d, f);
+        }
+    }
+    // thread 0 keeps the descriptor of the next block to issue in registers (its loads overlap one iteration)
+    unsigned long long nd_r0 = 0, nd_r1 = 0, nd_n0 = 0, nd_n1 = 0;
+    unsigned nd_fl = 0;
+    unsigned issue_j = pro, issue_s = pro % stages;
+    auto fetch_next = [&]() {
+        if (issue_j < n_my) {
+            const size_t b = blk(issue_j);
+            nd_r0 = (unsigned long long)__ldg(blk_rows + b); nd_r1 = (unsigned long long)__ldg(blk_rows + b + 1);
+            nd_n0 = (unsigned long long)__ldg(blk_nnz + b); nd_n1 = (unsigned long long)__ldg(blk_nnz + b + 1);
+            nd_fl = __ldg(blk_flags + b);
+        }
+    };
+    if (tid == 0) fetch_next();
+
+    double acc = 0.0;
+    unsigned s = 0, parity = 0;
+    for (unsigned i = 0; i < n_my; ++i) {
+        mbar_wait(&full[s], parity);
+        const uint64_t r0 = s_desc[s][0], r1 = s_desc[s][1], n0 = s_desc[s][2], n1 = s_desc[s][3];
+        const unsigned fl = s_flags[s];
+        const uint64_t a0 = n0 & ~(uint64_t)3;
+        T* sv = reinterpret_cast<T*>(smem_raw + (size_t)s * stage_bytes);
+        const I* sc = reinterpret_cast<const I*>(smem_raw + (size_t)s * stage_bytes + (size_t)cap * sizeof(T));
+        // row offsets of the rows this thread will sum: requested now, needed after the barrier
+        unsigned oa[K], oe[K];
+        if (!(fl & (kBlkNoFit | kBlkLong))) {
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                const uint64_t r = r0 + tid + (uint64_t)j * THREADS;
+                oa[j] = oe[j] = 0;
+                if (r < r1) {
+                    oa[j] = (unsigned)((uint64_t)__ldg(offs + r) - a0);
+                    oe[j] = (unsigned)((uint64_t)__ldg(offs + r + 1) - a0);
+                }
+            }
+        }
+        if (!(fl & kBlkNoFit)) {
+            const unsigned groups = (unsigned)(((n1 - a0) + 3) & ~(uint64_t)3) / G;
+            for (unsigned g = tid; g < groups; g += THREADS * U) {
+                Grp<I, G> c[U];
+                Grp<T, G> v[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const unsigned gi = g + u * THREADS;
+                    if (gi < groups) { c[u] = lds_grp<I, G>(sc + (size_t)gi * G); v[u] = lds_grp<T, G>(sv + (size_t)gi * G); }
+                }
+                Grp<T, G> xv[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (g + u * THREADS < groups) {
+#pragma unroll
+                        for (int k = 0; k < G; ++k) xv[u].e[k] = __ldg(x + (size_t)c[u].e[k]);
+                    }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const unsigned gi = g + u * THREADS;
+                    if (gi < groups) {
+#pragma unroll
+                        for (int k = 0; k < G; ++k) v[u].e[k] = mul_rn(xv[u].e[k], v[u].e[k]);
+                        sts_grp<T, G>(sv + (size_t)gi * G, v[u]);
+                    }
+                }
+            }
+            fence_proxy_async();      // the products were written through the generic proxy; the refill is async-proxy
+        }
+        __syncthreads();
+        if (tid == 0 && issue_j < n_my) {
+            // the stage consumed in iteration i - 1 is free now
+            issue(issue_s, nd_r0, nd_r1, nd_n0, nd_n1, nd_fl);
+            ++issue_j;
+            if (++issue_s == stages) issue_s = 0;
+            fetch_next();
+        }
+        if (fl & kBlkNoFit) {
+            acc += rows_direct<T, I, DOT, THREADS>(vals, cols, offs, r0, r1, x, y, (const T*)dot.w, &s_long_count, s_long_rows, scratch);
+            __syncthreads();
+            if (tid == 0) s_long_count = 0;
+        } else if (fl & kBlkLong) {
+            acc += reduce_rows_from_smem<T, I, DOT, THREADS>(sv, offs, r0, r1, a0, y, (const T*)dot.w, &s_long_count, s_long_rows);
+            __syncthreads();
+            if (tid == 0) s_long_count = 0;
+        } else {
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                const uint64_t r = r0 + tid + (uint64_t)j * THREADS;
+                if (r < r1) {
+                    T sum = T(0);
+                    for (unsigned k = oa[j]; k < oe[j]; ++k) sum = add_rn(sum, sv[k]);
+                    y[r] = sum;
+                    if constexpr (DOT) acc += (double)mul_rn(__ldg((const T*)dot.w + r), sum);
+                }
+            }
+            for (uint64_t r = r0 + tid + (uint64_t)K * THREADS; r < r1; r += THREADS) {
+                const unsigned a = (unsigned)((uint64_t)__ldg(offs + r) - a0), e = (unsigned)((uint64_t)__ldg(offs + r + 1) - a0);
+                T sum = T(0);
+                for (unsigned k = a; k < e; ++k) sum = add_rn(sum, sv[k]);
+                y[r] = sum;
+                if constexpr (DOT) acc += (double)mul_rn(__ldg((const T*)dot.w + r), sum);
+            }
+        }
+        if (++s == stages) { s = 0; parity ^= 1u; }
+    }
+    if constexpr (DOT) finish_dot<T, THREADS>(acc, dot);
+}
+
 // ---- plan construction --------------------------------------------------------------------------------
 // Split points of the merge coordinate key(r) = (r - rb) + (offs[r] - offs[rb]) at multiples of `target`.
 template <class I>
 __global__ void split_rows_kernel(const I* __restrict__ offs, uint64_t rb, uint64_t re, uint64_t target, uint64_t n_blocks,
-                                  I* __restrict__ blk_rows) {
+                                  I* __restrict__ blk_rows, I* __restrict__ blk_nnz) {
     const uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (k > n_blocks) return;
-    if (k == n_blocks) { blk_rows[k] = (I)re; return; }
+    if (k == n_blocks) { blk_rows[k] = (I)re; blk_nnz[k] = offs[re]; return; }
     const uint64_t base = (uint64_t)offs[rb];
     const uint64_t want = k * target;
     uint64_t lo = rb, hi = re;          // smallest r in [rb,re] with key(r) >= want
@@ -393,6 +584,25 @@ __global__ void split_rows_kernel(const I* __restrict__ offs, uint64_t rb, uint6
         if (key < want) lo = mid + 1; else hi = mid;
     }
     blk_rows[k] = (I)lo;
+    blk_nnz[k] = offs[lo];
+}
+
+// PIPE: per block, does the slice fit a stage and does it hold a row longer than kWarpRowMin?
+template <class I>
+__global__ void block_flags_kernel(const I* __restrict__ offs, const I* __restrict__ blk_rows, uint64_t n_blocks, unsigned cap,
+                                   unsigned char* __restrict__ flags) {
+    const uint64_t b = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (b >= n_blocks) return;
+    const uint64_t r0 = (uint64_t)blk_rows[b], r1 = (uint64_t)blk_rows[b + 1];
+    const uint64_t n0 = (uint64_t)offs[r0], n1 = (uint64_t)offs[r1];
+    unsigned f = (n1 - (n0 & ~(uint64_t)3)) > (uint64_t)cap ? kBlkNoFit : 0u;
+    uint64_t prev = n0;
+    for (uint64_t r = r0; r < r1; ++r) {
+        const uint64_t e = (uint64_t)offs[r + 1];
+        if (e - prev > (uint64_t)kWarpRowMin) { f |= kBlkLong; break; }
+        prev = e;
+    }
+    flags[b] = (unsigned char)f;
 }
 
 // Per block: [min column, max column + 1) over the block's own elements.
@@ -428,6 +638,8 @@ block_window_kernel(const I* __restrict__ cols, const I* __restrict__ offs, cons
 
 void plan_free(SpmvPlan& p) {
     if (p.blk_rows) cudaFree(p.blk_rows);
+    if (p.blk_nnz) cudaFree(p.blk_nnz);
+    if (p.blk_flags) cudaFree(p.blk_flags);
     if (p.blk_win) cudaFree(p.blk_win);
     p = SpmvPlan();
 }
@@ -452,6 +664,11 @@ static void stream_shape(const smb200_crs* m, int variant, unsigned* cap, unsign
     unsigned c, t;
     if (variant == SMB200_SPMV_STREAM) {
         c = m->vt == SMB200_F64 ? 3072u : 4608u;
+    } else if (variant == SMB200_SPMV_STREAM_PIPE) {
+        // one ring stage: 32 KB of values + columns
+        const size_t per = vsize(m->vt) + isize(m->it);
+        c = (unsigned)((32u * 1024u) / per) & ~3u;
+        c = (unsigned)env_int("SMB200_PIPE_CAP", (int)c) & ~3u;
     } else {
         // TMA variants stage values + columns: keep the footprint comparable
         const size_t per = vsize(m->vt) + isize(m->it);
@@ -459,6 +676,7 @@ static void stream_shape(const smb200_crs* m, int variant, unsigned* cap, unsign
     }
     c = (unsigned)env_int("SMB200_STREAM_CAP", (int)c) & ~3u;
     if (c < 256) c = 256;
+    if (c > kMaxCap) c = kMaxCap;
     t = c - c / 9;                     // leave room for the row that straddles the target
     t = (unsigned)env_int("SMB200_STREAM_TARGET", (int)t);
     if (t + 8 > c) t = c - 8;
@@ -469,7 +687,8 @@ static void stream_shape(const smb200_crs* m, int variant, unsigned* cap, unsign
 struct PlanShape { unsigned cap = 0, target = 0, win_cap = 0; };
 static PlanShape g_shape_of_plan(const smb200_crs* m, const SpmvPlan& p) {
     PlanShape s;
-    if (p.variant >= SMB200_SPMV_STREAM) stream_shape(m, p.variant, &s.cap, &s.target);
+    s.cap = p.cap;
+    s.target = p.target;
     if (p.variant == SMB200_SPMV_BANDED) {
         const unsigned xa = (unsigned)(16 / vsize(m->vt));
         s.win_cap = (unsigned)((p.max_win + 2 * xa) & ~(uint64_t)(xa - 1));
@@ -504,6 +723,8 @@ smb200_status plan_build_range(smb200_crs* m, SpmvPlan& p, int want_variant, int
     if (variant >= SMB200_SPMV_STREAM && rows > 0) {
         unsigned cap, target;
         stream_shape(m, variant, &cap, &target);
+        p.cap = cap;
+        p.target = target;
         // total merge length of the range, from the two boundary offsets
         uint64_t ob = 0, oe = 0;
         const size_t is = isize(m->it);
@@ -523,11 +744,20 @@ smb200_status plan_build_range(smb200_crs* m, SpmvPlan& p, int want_variant, int
         if (p.n_blocks == 0) p.n_blocks = 1;
         SMB_REQUIRE(p.n_blocks < 0x7FFFFFFFull, SMB200_ERR_UNSUPPORTED, "spmv: too many row blocks");
         SMB_CUDA(cudaMalloc(&p.blk_rows, (p.n_blocks + 1) * is));
+        SMB_CUDA(cudaMalloc(&p.blk_nnz, (p.n_blocks + 1) * is));
         const unsigned g = (unsigned)((p.n_blocks + 1 + 255) / 256);
-        if (m->it == SMB200_U64) split_rows_kernel<uint64_t><<<g, 256, 0, ctx->stream>>>((const uint64_t*)m->offsets, rb, re, target, p.n_blocks, (uint64_t*)p.blk_rows);
-        else split_rows_kernel<uint32_t><<<g, 256, 0, ctx->stream>>>((const uint32_t*)m->offsets, rb, re, target, p.n_blocks, (uint32_t*)p.blk_rows);
+        if (m->it == SMB200_U64) split_rows_kernel<uint64_t><<<g, 256, 0, ctx->stream>>>((const uint64_t*)m->offsets, rb, re, target, p.n_blocks, (uint64_t*)p.blk_rows, (uint64_t*)p.blk_nnz);
+        else split_rows_kernel<uint32_t><<<g, 256, 0, ctx->stream>>>((const uint32_t*)m->offsets, rb, re, target, p.n_blocks, (uint32_t*)p.blk_rows, (uint32_t*)p.blk_nnz);
         count_launch();
         SMB_CUDA(cudaGetLastError());
+        if (variant == SMB200_SPMV_STREAM_PIPE) {
+            SMB_CUDA(cudaMalloc(&p.blk_flags, p.n_blocks));
+            const unsigned gf = (unsigned)((p.n_blocks + 127) / 128);
+            if (m->it == SMB200_U64) block_flags_kernel<uint64_t><<<gf, 128, 0, ctx->stream>>>((const uint64_t*)m->offsets, (const uint64_t*)p.blk_rows, p.n_blocks, cap, p.blk_flags);
+            else block_flags_kernel<uint32_t><<<gf, 128, 0, ctx->stream>>>((const uint32_t*)m->offsets, (const uint32_t*)p.blk_rows, p.n_blocks, cap, p.blk_flags);
+            count_launch();
+            SMB_CUDA(cudaGetLastError());
+        }
         if (variant == SMB200_SPMV_BANDED) {
             SMB_CUDA(cudaMalloc(&p.blk_win, 2 * p.n_blocks * is));
             unsigned long long* d_max = nullptr;
@@ -591,6 +821,28 @@ static smb200_status launch_typed(smb200_crs* m, const SpmvPlan& p, uint64_t rb,
             if (smem > 48 * 1024) SMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             if (carve >= 0) SMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
             kern<<<(unsigned)p.n_blocks, kSpmvThreads, smem, st>>>(vals, cols, offs, (const I*)p.blk_rows, sh.cap, xx, yy, dot);
+        } else if (p.variant == SMB200_SPMV_STREAM_PIPE) {
+            int stages = env_int("SMB200_PIPE_STAGES", 3);
+            if (stages < 2) stages = 2;
+            if (stages > kPipeMaxStages) stages = kPipeMaxStages;
+            const size_t per_stage = (size_t)sh.cap * (sizeof(T) + sizeof(I));
+            while (stages > 2 && per_stage * stages > 200u * 1024u) --stages;
+            const size_t smem = per_stage * stages;
+            SMB_REQUIRE(smem <= 227u * 1024u, SMB200_ERR_INVALID, "spmv: pipeline stage of %zu bytes does not fit shared memory", per_stage);
+            int ctas = env_int("SMB200_PIPE_CTAS", 0);
+            if (ctas <= 0) { ctas = (int)((220u * 1024u) / (smem + 2048)); if (ctas < 1) ctas = 1; if (ctas > 4) ctas = 4; }
+            const int threads = env_int("SMB200_PIPE_THREADS", 256);
+            uint64_t grid = (uint64_t)ctx->sm_count * (uint64_t)ctas;
+            if (grid > p.n_blocks) grid = p.n_blocks;
+            if (threads == 512) {
+                auto kern = spmv_pipe_kernel<T, I, 512, DOT>;
+                SMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                kern<<<(unsigned)grid, 512, smem, st>>>(vals, cols, offs, (const I*)p.blk_rows, (const I*)p.blk_nnz, p.blk_flags, (unsigned)p.n_blocks, sh.cap, (unsigned)stages, xx, yy, dot);
+            } else {
+                auto kern = spmv_pipe_kernel<T, I, 256, DOT>;
+                SMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                kern<<<(unsigned)grid, 256, smem, st>>>(vals, cols, offs, (const I*)p.blk_rows, (const I*)p.blk_nnz, p.blk_flags, (unsigned)p.n_blocks, sh.cap, (unsigned)stages, xx, yy, dot);
+            }
         } else if (p.variant == SMB200_SPMV_STREAM_TMA) {
             const size_t smem = (size_t)sh.cap * (sizeof(T) + sizeof(I));
             auto kern = spmv_stream_tma_kernel<T, I, DOT, false>;
@@ -688,7 +940,7 @@ extern "C" {
 
 smb200_status smb200_crs_configure(smb200_crs* m, smb200_spmv_variant variant, int32_t lanes, uint32_t flags) {
     SMB_REQUIRE(m, SMB200_ERR_INVALID, "crs_configure: NULL argument");
-    SMB_REQUIRE(variant >= SMB200_SPMV_AUTO && variant <= SMB200_SPMV_BANDED, SMB200_ERR_INVALID, "crs_configure: bad variant %d", (int)variant);
+    SMB_REQUIRE(variant >= SMB200_SPMV_AUTO && variant <= SMB200_SPMV_STREAM_PIPE, SMB200_ERR_INVALID, "crs_configure: bad variant %d", (int)variant);
     m->want_variant = variant;
     m->want_lanes = lanes;
     m->want_flags = flags;

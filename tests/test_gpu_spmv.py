@@ -17,7 +17,7 @@ COMBOS = [(F32, U32), (F64, U32), (F32, U64), (F64, U64)]
 
 def _variants(smb):
     return [(smb.SPMV_SCALAR, 0), (smb.SPMV_VECTOR, 2), (smb.SPMV_VECTOR, 4), (smb.SPMV_VECTOR, 8), (smb.SPMV_VECTOR, 16),
-            (smb.SPMV_VECTOR, 32), (smb.SPMV_STREAM, 0), (smb.SPMV_STREAM_TMA, 0), (smb.SPMV_BANDED, 0), (smb.SPMV_AUTO, 0)]
+            (smb.SPMV_VECTOR, 32), (smb.SPMV_STREAM, 0), (smb.SPMV_STREAM_TMA, 0), (smb.SPMV_BANDED, 0), (smb.SPMV_STREAM_PIPE, 0), (smb.SPMV_AUTO, 0)]
 
 
 def _check(smb, orc, ctx, case, seed=11, x_extra=0):
@@ -101,7 +101,7 @@ def test_reference_known_answers(smb, ctx):
     a = smb.SparseMatCRS.from_raw_parts(ctx, 3, 3, np.array([4.2, 0.12, 7.12, 4.12, 2.24, 2.12], F32),
                                         np.array([1, 2, 0, 2, 1, 2], U32), np.array([0, 3, 5, 6], U32))
     v = smb.DenseVec.from_vec(ctx, np.array([2.0, 4.8, 1.2], F32))
-    for variant in (smb.SPMV_AUTO, smb.SPMV_SCALAR, smb.SPMV_STREAM, smb.SPMV_STREAM_TMA, smb.SPMV_BANDED):
+    for variant in (smb.SPMV_AUTO, smb.SPMV_SCALAR, smb.SPMV_STREAM, smb.SPMV_STREAM_TMA, smb.SPMV_BANDED, smb.SPMV_STREAM_PIPE):
         a.configure(variant)
         assert (a * v).get(0) == F32(34.544)
     assert a.density() == 6.0 / 9.0                                        # lib.rs:83
@@ -153,7 +153,7 @@ def test_full_size_headline_workload_properties(smb, ctx):
     x = smb.DenseVec(ctx, n ** 3, F32)
     x.fill_uniform(2)
     ref = None
-    for variant in (smb.SPMV_STREAM, smb.SPMV_STREAM_TMA, smb.SPMV_SCALAR, smb.SPMV_AUTO):
+    for variant in (smb.SPMV_STREAM, smb.SPMV_STREAM_TMA, smb.SPMV_STREAM_PIPE, smb.SPMV_SCALAR, smb.SPMV_AUTO):
         a.configure(variant)
         got = a.mvp(x).to_numpy()
         if ref is None:
