@@ -37,6 +37,8 @@ constexpr int kLongCap = 192;        // per-CTA list of rows deferred to the war
 constexpr unsigned kMaxCap = 12288;  // staging capacity limit implied by kLongCap
 constexpr unsigned kBlkNoFit = 1u;   // PIPE block flags: slice larger than a stage -> direct path
 constexpr unsigned kBlkLong = 2u;    //                   a row of more than kWarpRowMin entries -> two-pass row sums
+constexpr unsigned kBlkShort = 4u;   //                   every row has <= kRowMajorMax entries -> row-major path
+constexpr int kRowMajorMax = 32;
 constexpr int kPipeMaxStages = 8;
 
 struct DotArgs {
@@ -404,8 +406,10 @@ template <class E, int G> __device__ __forceinline__ void sts_grp(E* p, const Gr
     else { uint2 v; memcpy(&v, q.e, 8); *reinterpret_cast<uint2*>(p) = v; }
 }
 
-template <class T, class I, int THREADS, bool DOT>
-__global__ void __launch_bounds__(THREADS)
+// ROWS = true: every row of the matrix has <= kRowMajorMax entries (stencils, FEM): only the row-major path is
+// compiled in, which keeps the kernel lean enough for two 256-thread CTAs per SM.  ROWS = false: general rows.
+template <class T, class I, int THREADS, bool DOT, bool ROWS>
+__global__ void __launch_bounds__(THREADS, 512 / THREADS)
 spmv_pipe_kernel(const T* __restrict__ vals, const I* __restrict__ cols, const I* __restrict__ offs,
                  const I* __restrict__ blk_rows, const I* __restrict__ blk_nnz, const unsigned char* __restrict__ blk_flags,
                  unsigned n_blocks, unsigned cap, unsigned stages, const T* __restrict__ x, T* __restrict__ y, DotArgs dot) {
@@ -418,7 +422,8 @@ spmv_pipe_kernel(const T* __restrict__ vals, const I* __restrict__ cols, const I
     __shared__ double scratch[THREADS / 32 + 1];
     constexpr int G = 16 / (sizeof(T) > sizeof(I) ? sizeof(T) : sizeof(I));   // elements per 16-byte group
     constexpr int U = 4;                                                        // groups in flight per thread
-    constexpr int K = 3;                                                        // rows per thread with prefetched offsets
+    constexpr int K = sizeof(T) == 4 ? 3 : 2;                                   // rows per thread with prefetched offsets
+    constexpr int CH = 8;                                                       // row-major path: entries per row in flight
     if constexpr (DOT) { if (solver_done(dot)) return; }
     const unsigned tid = threadIdx.x;
     const unsigned n_my = blockIdx.x < n_blocks ? (n_blocks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
@@ -453,7 +458,7 @@ spmv_pipe_kernel(const T* __restrict__ vals, const I* __restrict__ cols, const I
             const size_t b = blk(tid);
             r0 = (unsigned long long)__ldg(blk_rows + b); r1 = (unsigned long long)__ldg(blk_rows + b + 1);
             n0 = (unsigned long long)__ldg(blk_nnz + b); n1 = (unsigned long long)__ldg(blk_nnz + b + 1);
-            fl = __ldg(blk_flags + b);
+            fl = ROWS ? 0u : __ldg(blk_flags + b);
         }
         for (unsigned j = 0; j < pro; ++j) {
             const unsigned long long a = __shfl_sync(0xffffffffu, r0, j), b2 = __shfl_sync(0xffffffffu, r1, j);
@@ -471,10 +476,25 @@ spmv_pipe_kernel(const T* __restrict__ vals, const I* __restrict__ cols, const I
             const size_t b = blk(issue_j);
             nd_r0 = (unsigned long long)__ldg(blk_rows + b); nd_r1 = (unsigned long long)__ldg(blk_rows + b + 1);
             nd_n0 = (unsigned long long)__ldg(blk_nnz + b); nd_n1 = (unsigned long long)__ldg(blk_nnz + b + 1);
-            nd_fl = __ldg(blk_flags + b);
+            nd_fl = ROWS ? 0u : __ldg(blk_flags + b);
         }
     };
     if (tid == 0) fetch_next();
+    __syncthreads();          // the prologue's descriptors are visible to everybody
+
+    // Row offsets of the K rows this thread sums per block, fetched ONE BLOCK AHEAD (raw values; they are only
+    // touched after the next barrier, so their DRAM latency overlaps a whole iteration).
+    I nxa[K], nxe[K];
+    auto fetch_offsets = [&](unsigned st) {
+        const uint64_t q0 = s_desc[st][0], q1 = s_desc[st][1];
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const uint64_t r = q0 + tid + (uint64_t)j * THREADS;
+            nxa[j] = nxe[j] = 0;
+            if (r < q1) { nxa[j] = __ldg(offs + r); nxe[j] = __ldg(offs + r + 1); }
+        }
+    };
+    if (n_my) fetch_offsets(0);
 
     double acc = 0.0;
     unsigned s = 0, parity = 0;
@@ -485,20 +505,52 @@ spmv_pipe_kernel(const T* __restrict__ vals, const I* __restrict__ cols, const I
         const uint64_t a0 = n0 & ~(uint64_t)3;
         T* sv = reinterpret_cast<T*>(smem_raw + (size_t)s * stage_bytes);
         const I* sc = reinterpret_cast<const I*>(smem_raw + (size_t)s * stage_bytes + (size_t)cap * sizeof(T));
-        // row offsets of the rows this thread will sum: requested now, needed after the barrier
-        unsigned oa[K], oe[K];
-        if (!(fl & (kBlkNoFit | kBlkLong))) {
+        I cua[K], cue[K];
+#pragma unroll
+        for (int j = 0; j < K; ++j) { cua[j] = nxa[j]; cue[j] = nxe[j]; }
+        if constexpr (ROWS) {
+            // Short rows (stencils): one thread per row straight out of the staged slice.  Lanes of a warp hold
+            // consecutive rows, so for a stencil the x gathers of one instruction fall into one or two cache lines,
+            // and the slice is read with an odd word stride (no bank conflicts).  Storage-order sums: bit-exact.
+            unsigned ka[K], ke[K];
+            I c[K][CH];
+            T v[K][CH], sum[K];
 #pragma unroll
             for (int j = 0; j < K; ++j) {
+                const bool live = r0 + tid + (uint64_t)j * THREADS < r1;
+                ka[j] = live ? (unsigned)((uint64_t)cua[j] - a0) : 0u;
+                ke[j] = live ? (unsigned)((uint64_t)cue[j] - a0) : 0u;
+                sum[j] = T(0);
+#pragma unroll
+                for (int u = 0; u < CH; ++u)
+                    if (ka[j] + u < ke[j]) { c[j][u] = sc[ka[j] + u]; v[j][u] = sv[ka[j] + u]; }
+            }
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+#pragma unroll
+                for (int u = 0; u < CH; ++u)
+                    if (ka[j] + u < ke[j]) v[j][u] = mul_rn(__ldg(x + (size_t)c[j][u]), v[j][u]);
+            }
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+#pragma unroll
+                for (int u = 0; u < CH; ++u)
+                    if (ka[j] + u < ke[j]) sum[j] = add_rn(sum[j], v[j][u]);
+                for (unsigned k = ka[j] + CH; k < ke[j]; ++k) sum[j] = add_rn(sum[j], mul_rn(__ldg(x + (size_t)sc[k]), sv[k]));
                 const uint64_t r = r0 + tid + (uint64_t)j * THREADS;
-                oa[j] = oe[j] = 0;
                 if (r < r1) {
-                    oa[j] = (unsigned)((uint64_t)__ldg(offs + r) - a0);
-                    oe[j] = (unsigned)((uint64_t)__ldg(offs + r + 1) - a0);
+                    y[r] = sum[j];
+                    if constexpr (DOT) acc += (double)mul_rn(__ldg((const T*)dot.w + r), sum[j]);
                 }
             }
-        }
-        if (!(fl & kBlkNoFit)) {
+            for (uint64_t r = r0 + tid + (uint64_t)K * THREADS; r < r1; r += THREADS) {
+                const unsigned a = (unsigned)((uint64_t)__ldg(offs + r) - a0), e = (unsigned)((uint64_t)__ldg(offs + r + 1) - a0);
+                T s1 = T(0);
+                for (unsigned k = a; k < e; ++k) s1 = add_rn(s1, mul_rn(__ldg(x + (size_t)sc[k]), sv[k]));
+                y[r] = s1;
+                if constexpr (DOT) acc += (double)mul_rn(__ldg((const T*)dot.w + r), s1);
+            }
+        } else if (!(fl & kBlkNoFit)) {
             const unsigned groups = (unsigned)(((n1 - a0) + 3) & ~(uint64_t)3) / G;
             for (unsigned g = tid; g < groups; g += THREADS * U) {
                 Grp<I, G> c[U];
@@ -535,7 +587,10 @@ spmv_pipe_kernel(const T* __restrict__ vals, const I* __restrict__ cols, const I
             if (++issue_s == stages) issue_s = 0;
             fetch_next();
         }
-        if (fl & kBlkNoFit) {
+        // block i + 1 was published before the barrier above: request its row offsets now
+        if (i + 1 < n_my) fetch_offsets(s + 1 == stages ? 0 : s + 1);
+        if constexpr (ROWS) {
+        } else if (fl & kBlkNoFit) {
             acc += rows_direct<T, I, DOT, THREADS>(vals, cols, offs, r0, r1, x, y, (const T*)dot.w, &s_long_count, s_long_rows, scratch);
             __syncthreads();
             if (tid == 0) s_long_count = 0;
@@ -549,7 +604,8 @@ spmv_pipe_kernel(const T* __restrict__ vals, const I* __restrict__ cols, const I
                 const uint64_t r = r0 + tid + (uint64_t)j * THREADS;
                 if (r < r1) {
                     T sum = T(0);
-                    for (unsigned k = oa[j]; k < oe[j]; ++k) sum = add_rn(sum, sv[k]);
+                    const unsigned ka = (unsigned)((uint64_t)cua[j] - a0), ke = (unsigned)((uint64_t)cue[j] - a0);
+                    for (unsigned k = ka; k < ke; ++k) sum = add_rn(sum, sv[k]);
                     y[r] = sum;
                     if constexpr (DOT) acc += (double)mul_rn(__ldg((const T*)dot.w + r), sum);
                 }
@@ -596,12 +652,15 @@ __global__ void block_flags_kernel(const I* __restrict__ offs, const I* __restri
     const uint64_t r0 = (uint64_t)blk_rows[b], r1 = (uint64_t)blk_rows[b + 1];
     const uint64_t n0 = (uint64_t)offs[r0], n1 = (uint64_t)offs[r1];
     unsigned f = (n1 - (n0 & ~(uint64_t)3)) > (uint64_t)cap ? kBlkNoFit : 0u;
-    uint64_t prev = n0;
+    uint64_t prev = n0, longest = 0;
     for (uint64_t r = r0; r < r1; ++r) {
         const uint64_t e = (uint64_t)offs[r + 1];
-        if (e - prev > (uint64_t)kWarpRowMin) { f |= kBlkLong; break; }
+        longest = e - prev > longest ? e - prev : longest;
+        if (longest > (uint64_t)kWarpRowMin) break;
         prev = e;
     }
+    if (longest > (uint64_t)kWarpRowMin) f |= kBlkLong;
+    else if (longest <= (uint64_t)kRowMajorMax && !(f & kBlkNoFit)) f |= kBlkShort;
     flags[b] = (unsigned char)f;
 }
 
@@ -823,10 +882,10 @@ static smb200_status launch_typed(smb200_crs* m, const SpmvPlan& p, uint64_t rb,
             kern<<<(unsigned)p.n_blocks, kSpmvThreads, smem, st>>>(vals, cols, offs, (const I*)p.blk_rows, sh.cap, xx, yy, dot);
         } else if (p.variant == SMB200_SPMV_STREAM_PIPE) {
             int stages = env_int("SMB200_PIPE_STAGES", 3);
-            if (stages < 2) stages = 2;
+            if (stages < 3) stages = 3;     // the kernel reads the descriptor of block i + 1 during iteration i
             if (stages > kPipeMaxStages) stages = kPipeMaxStages;
             const size_t per_stage = (size_t)sh.cap * (sizeof(T) + sizeof(I));
-            while (stages > 2 && per_stage * stages > 200u * 1024u) --stages;
+            while (stages > 3 && per_stage * stages > 200u * 1024u) --stages;
             const size_t smem = per_stage * stages;
             SMB_REQUIRE(smem <= 227u * 1024u, SMB200_ERR_INVALID, "spmv: pipeline stage of %zu bytes does not fit shared memory", per_stage);
             int ctas = env_int("SMB200_PIPE_CTAS", 0);
@@ -834,15 +893,21 @@ static smb200_status launch_typed(smb200_crs* m, const SpmvPlan& p, uint64_t rb,
             const int threads = env_int("SMB200_PIPE_THREADS", 256);
             uint64_t grid = (uint64_t)ctx->sm_count * (uint64_t)ctas;
             if (grid > p.n_blocks) grid = p.n_blocks;
-            if (threads == 512) {
-                auto kern = spmv_pipe_kernel<T, I, 512, DOT>;
-                SMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                kern<<<(unsigned)grid, 512, smem, st>>>(vals, cols, offs, (const I*)p.blk_rows, (const I*)p.blk_nnz, p.blk_flags, (unsigned)p.n_blocks, sh.cap, (unsigned)stages, xx, yy, dot);
-            } else {
-                auto kern = spmv_pipe_kernel<T, I, 256, DOT>;
-                SMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                kern<<<(unsigned)grid, 256, smem, st>>>(vals, cols, offs, (const I*)p.blk_rows, (const I*)p.blk_nnz, p.blk_flags, (unsigned)p.n_blocks, sh.cap, (unsigned)stages, xx, yy, dot);
-            }
+            const bool rows_mode = m->max_row_len <= (uint64_t)kRowMajorMax && env_int("SMB200_PIPE_ROWS", 1) != 0;
+#define SMB_PIPE_LAUNCH(TH, RW)                                                                                          \
+    do {                                                                                                                 \
+        auto kern = spmv_pipe_kernel<T, I, TH, DOT, RW>;                                                                 \
+        SMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                    \
+        int resident = 0;                                                                                                \
+        SMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, TH, smem));                              \
+        if (resident < 1) resident = 1;                                                                                  \
+        if ((uint64_t)resident * ctx->sm_count < grid) grid = (uint64_t)resident * ctx->sm_count;                        \
+        kern<<<(unsigned)grid, TH, smem, st>>>(vals, cols, offs, (const I*)p.blk_rows, (const I*)p.blk_nnz, p.blk_flags, \
+                                               (unsigned)p.n_blocks, sh.cap, (unsigned)stages, xx, yy, dot);            \
+    } while (0)
+            if (threads == 512) { if (rows_mode) SMB_PIPE_LAUNCH(512, true); else SMB_PIPE_LAUNCH(512, false); }
+            else { if (rows_mode) SMB_PIPE_LAUNCH(256, true); else SMB_PIPE_LAUNCH(256, false); }
+#undef SMB_PIPE_LAUNCH
         } else if (p.variant == SMB200_SPMV_STREAM_TMA) {
             const size_t smem = (size_t)sh.cap * (sizeof(T) + sizeof(I));
             auto kern = spmv_stream_tma_kernel<T, I, DOT, false>;
