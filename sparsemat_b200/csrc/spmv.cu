@@ -101,14 +101,19 @@ spmv_vector_kernel(const T* __restrict__ vals, const I* __restrict__ cols, const
 // 4 consecutive elements of an array, 16-byte (T,I of 4 bytes) or 32-byte (8 bytes) aligned.
 template <class E> struct Quad { E e[4]; };
 
+// Streamed once: bypass L1 (it is kept for the x gathers) and mark the line evict-first in L2.  8-byte element
+// quads are one 256-bit load (LDG.E.256, new on sm_100).
 template <class E> __device__ __forceinline__ Quad<E> load_quad_stream(const E* p) {
     Quad<E> q;
     if constexpr (sizeof(E) == 4) {
-        const uint4 v = __ldcs(reinterpret_cast<const uint4*>(p));
+        uint4 v;
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
         memcpy(q.e, &v, 16);
     } else {
-        const uint4 v0 = __ldcs(reinterpret_cast<const uint4*>(p));
-        const uint4 v1 = __ldcs(reinterpret_cast<const uint4*>(p) + 1);
+        uint4 v0, v1;
+        asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(v0.x), "=r"(v0.y), "=r"(v0.z), "=r"(v0.w), "=r"(v1.x), "=r"(v1.y), "=r"(v1.z), "=r"(v1.w) : "l"(p));
         memcpy(q.e, &v0, 16);
         memcpy(q.e + 2, &v1, 16);
     }
@@ -230,7 +235,8 @@ __device__ __forceinline__ double rows_direct(const T* __restrict__ vals, const 
 template <class T, class I, bool DOT>
 __global__ void __launch_bounds__(kSpmvThreads)
 spmv_stream_kernel(const T* __restrict__ vals, const I* __restrict__ cols, const I* __restrict__ offs,
-                   const I* __restrict__ blk_rows, unsigned cap, const T* __restrict__ x, T* __restrict__ y, DotArgs dot) {
+                   const I* __restrict__ blk_rows, const I* __restrict__ blk_nnz, unsigned cap, const T* __restrict__ x,
+                   T* __restrict__ y, DotArgs dot) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     T* prod = reinterpret_cast<T*>(smem_raw);
     __shared__ unsigned int s_long_count;
@@ -238,10 +244,21 @@ spmv_stream_kernel(const T* __restrict__ vals, const I* __restrict__ cols, const
     __shared__ double scratch[kSpmvThreads / 32 + 1];
     if constexpr (DOT) { if (solver_done(dot)) return; }
     if (threadIdx.x == 0) s_long_count = 0;
+    // one round trip for the block's row range and element range (the plan stores offset_rows[blk_rows[k]])
     const uint64_t r0 = (uint64_t)__ldg(blk_rows + blockIdx.x), r1 = (uint64_t)__ldg(blk_rows + blockIdx.x + 1);
-    const uint64_t n0 = (uint64_t)__ldg(offs + r0), n1 = (uint64_t)__ldg(offs + r1);
+    const uint64_t n0 = (uint64_t)__ldg(blk_nnz + blockIdx.x), n1 = (uint64_t)__ldg(blk_nnz + blockIdx.x + 1);
     const uint64_t a0 = n0 & ~(uint64_t)3;
     double acc = 0.0;
+    // Row offsets of the first two rows this thread will sum: requested before the stream loads, first touched
+    // after the barrier, so their latency hides behind the whole product phase.
+    constexpr int KP = 2;
+    I pfa[KP], pfe[KP];
+#pragma unroll
+    for (int j = 0; j < KP; ++j) {
+        const uint64_t r = r0 + threadIdx.x + (uint64_t)j * kSpmvThreads;
+        pfa[j] = pfe[j] = 0;
+        if (r < r1) { pfa[j] = __ldg(offs + r); pfe[j] = __ldg(offs + r + 1); }
+    }
     __syncthreads();
     if (n1 - a0 <= (uint64_t)cap) {
         const unsigned groups = (unsigned)((n1 - a0 + 3) >> 2);
@@ -273,7 +290,31 @@ spmv_stream_kernel(const T* __restrict__ vals, const I* __restrict__ cols, const
             store_quad_shared(prod + 4 * g, p0);
         }
         __syncthreads();
-        acc = reduce_rows_from_smem<T, I, DOT>(prod, offs, r0, r1, a0, y, (const T*)dot.w, &s_long_count, s_long_rows);
+        // rows whose offsets were prefetched and that are short enough for the storage-order sum
+        uint64_t r_next = r0;
+        bool all_short = true;
+        double acc_fast = 0.0;
+#pragma unroll
+        for (int j = 0; j < KP; ++j) {
+            const uint64_t r = r0 + threadIdx.x + (uint64_t)j * kSpmvThreads;
+            if (r < r1) {
+                const unsigned a = (unsigned)((uint64_t)pfa[j] - a0), e = (unsigned)((uint64_t)pfe[j] - a0);
+                if (e - a <= (unsigned)kWarpRowMin) {
+                    T sum = T(0);
+                    for (unsigned k = a; k < e; ++k) sum = add_rn(sum, prod[k]);
+                    y[r] = sum;
+                    if constexpr (DOT) acc_fast += (double)mul_rn(__ldg((const T*)dot.w + r), sum);
+                } else {
+                    all_short = false;
+                }
+            }
+        }
+        r_next = r0 + (uint64_t)KP * kSpmvThreads;
+        // everything else (rows beyond KP per thread, rows longer than kWarpRowMin) takes the generic two-pass path
+        if (__syncthreads_or(!all_short)) { r_next = r0; acc_fast = 0.0; }    // redo the block generically
+        acc = acc_fast;
+        if (r_next < r1)
+            acc += reduce_rows_from_smem<T, I, DOT>(prod, offs, r_next, r1, a0 + 0, y, (const T*)dot.w, &s_long_count, s_long_rows);
     } else {
         acc = rows_direct<T, I, DOT>(vals, cols, offs, r0, r1, x, y, (const T*)dot.w, &s_long_count, s_long_rows, scratch);
     }
@@ -722,7 +763,7 @@ static int pick_lanes(double mean_len) {
 static void stream_shape(const smb200_crs* m, int variant, unsigned* cap, unsigned* target) {
     unsigned c, t;
     if (variant == SMB200_SPMV_STREAM) {
-        c = m->vt == SMB200_F64 ? 3072u : 4608u;
+        c = m->vt == SMB200_F64 ? 3584u : 4608u;
     } else if (variant == SMB200_SPMV_STREAM_PIPE) {
         // one ring stage: 32 KB of values + columns
         const size_t per = vsize(m->vt) + isize(m->it);
@@ -879,7 +920,7 @@ static smb200_status launch_typed(smb200_crs* m, const SpmvPlan& p, uint64_t rb,
             auto kern = spmv_stream_kernel<T, I, DOT>;
             if (smem > 48 * 1024) SMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             if (carve >= 0) SMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-            kern<<<(unsigned)p.n_blocks, kSpmvThreads, smem, st>>>(vals, cols, offs, (const I*)p.blk_rows, sh.cap, xx, yy, dot);
+            kern<<<(unsigned)p.n_blocks, kSpmvThreads, smem, st>>>(vals, cols, offs, (const I*)p.blk_rows, (const I*)p.blk_nnz, sh.cap, xx, yy, dot);
         } else if (p.variant == SMB200_SPMV_STREAM_PIPE) {
             int stages = env_int("SMB200_PIPE_STAGES", 3);
             if (stages < 3) stages = 3;     // the kernel reads the descriptor of block i + 1 during iteration i
