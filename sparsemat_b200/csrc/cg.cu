@@ -25,7 +25,9 @@ namespace smb {
 // device scalar block (doubles)
 // S_PAP..S_PAP+2: up to three partial p.Ap sums (interior / lower / upper boundary launches of the
 // distributed SpMV); contiguous so one all-reduce covers them.  Single GPU uses slot 0 only.
-enum { S_RR = 0, S_PAP = 1, S_RR_NEW = 4, S_THRESH = 5, S_ITER = 6, S_DONE = 7, S_COUNT = 8 };
+// S_RR_LOCAL: multi-GPU only — the rank-local r.r, all-reduced OUT OF PLACE into S_RR_NEW (after the stop test
+// has fired the update kernels exit early and leave S_RR_LOCAL alone, so repeating the all-reduce is harmless).
+enum { S_RR = 0, S_PAP = 1, S_RR_NEW = 4, S_THRESH = 5, S_ITER = 6, S_DONE = 7, S_RR_LOCAL = 8, S_COUNT = 16 };
 
 constexpr int kCgThreads = 256;
 
@@ -33,7 +35,7 @@ constexpr int kCgThreads = 256;
 template <class T>
 __global__ void __launch_bounds__(kCgThreads)
 cg_init_kernel(const T* __restrict__ b, const T* __restrict__ ap, T* __restrict__ r, T* __restrict__ p, uint64_t n,
-               double* __restrict__ S, double* __restrict__ partials, unsigned int* __restrict__ ticket) {
+               double* __restrict__ S, int rr_slot, double* __restrict__ partials, unsigned int* __restrict__ ticket) {
     __shared__ double scratch[kCgThreads / 32 + 1];
     using V = typename Vec16<T>::type;
     constexpr int N = Vec16<T>::N;
@@ -66,14 +68,14 @@ cg_init_kernel(const T* __restrict__ b, const T* __restrict__ ap, T* __restrict_
     const double bsum = block_sum<kCgThreads>(acc, scratch);
     double total;
     if (grid_sum<kCgThreads>(bsum, partials, ticket, scratch, total))
-        if (threadIdx.x == 0) S[S_RR_NEW] = (double)(T)total;
+        if (threadIdx.x == 0) S[rr_slot] = (double)(T)total;
 }
 
 // B: x += (p * alpha); r -= (ap * alpha); S[RR_NEW] = r.r      (linearsolver.rs:45-51)
 template <class T>
 __global__ void __launch_bounds__(kCgThreads)
 cg_update_xr_kernel(T* __restrict__ x, T* __restrict__ r, const T* __restrict__ p, const T* __restrict__ ap, uint64_t n,
-                    double* __restrict__ S, double* __restrict__ partials, unsigned int* __restrict__ ticket) {
+                    double* __restrict__ S, int rr_slot, double* __restrict__ partials, unsigned int* __restrict__ ticket) {
     __shared__ double scratch[kCgThreads / 32 + 1];
     if (__ldcg(S + S_DONE) != 0.0) return;
     const T alpha = div_rn((T)__ldcg(S + S_RR), (T)(__ldcg(S + S_PAP) + __ldcg(S + S_PAP + 1) + __ldcg(S + S_PAP + 2)));
@@ -112,7 +114,7 @@ cg_update_xr_kernel(T* __restrict__ x, T* __restrict__ r, const T* __restrict__ 
     const double bsum = block_sum<kCgThreads>(acc, scratch);
     double total;
     if (grid_sum<kCgThreads>(bsum, partials, ticket, scratch, total))
-        if (threadIdx.x == 0) S[S_RR_NEW] = (double)(T)total;
+        if (threadIdx.x == 0) S[rr_slot] = (double)(T)total;
 }
 
 // C: stop test, bookkeeping, p = (p * beta) + r                  (linearsolver.rs:52-59)
@@ -189,8 +191,9 @@ smb200_status cg_prepare(smb200_ctx* ctx, CgWork& w, int vt, uint64_t n, uint64_
 
 smb200_status cg_init_launch(smb200_ctx* ctx, CgWork& w, int vt, const void* b, uint64_t n) {
     const unsigned g = cg_grid(ctx, n, vt);
-    if (vt == SMB200_F64) cg_init_kernel<double><<<g, kCgThreads, 0, ctx->stream>>>((const double*)b, (const double*)w.ap, (double*)w.r, (double*)w.p, n, w.scalars, ctx->red_partials, ctx->red_ticket);
-    else cg_init_kernel<float><<<g, kCgThreads, 0, ctx->stream>>>((const float*)b, (const float*)w.ap, (float*)w.r, (float*)w.p, n, w.scalars, ctx->red_partials, ctx->red_ticket);
+    const int slot = ctx->world > 1 ? S_RR_LOCAL : S_RR_NEW;
+    if (vt == SMB200_F64) cg_init_kernel<double><<<g, kCgThreads, 0, ctx->stream>>>((const double*)b, (const double*)w.ap, (double*)w.r, (double*)w.p, n, w.scalars, slot, ctx->red_partials, ctx->red_ticket);
+    else cg_init_kernel<float><<<g, kCgThreads, 0, ctx->stream>>>((const float*)b, (const float*)w.ap, (float*)w.r, (float*)w.p, n, w.scalars, slot, ctx->red_partials, ctx->red_ticket);
     count_launch();
     SMB_CUDA(cudaGetLastError());
     return SMB200_OK;
@@ -198,8 +201,9 @@ smb200_status cg_init_launch(smb200_ctx* ctx, CgWork& w, int vt, const void* b, 
 
 smb200_status cg_xr_launch(smb200_ctx* ctx, CgWork& w, int vt, void* x, uint64_t n) {
     const unsigned g = cg_grid(ctx, n, vt);
-    if (vt == SMB200_F64) cg_update_xr_kernel<double><<<g, kCgThreads, 0, ctx->stream>>>((double*)x, (double*)w.r, (const double*)w.p, (const double*)w.ap, n, w.scalars, ctx->red_partials, ctx->red_ticket);
-    else cg_update_xr_kernel<float><<<g, kCgThreads, 0, ctx->stream>>>((float*)x, (float*)w.r, (const float*)w.p, (const float*)w.ap, n, w.scalars, ctx->red_partials, ctx->red_ticket);
+    const int slot = ctx->world > 1 ? S_RR_LOCAL : S_RR_NEW;
+    if (vt == SMB200_F64) cg_update_xr_kernel<double><<<g, kCgThreads, 0, ctx->stream>>>((double*)x, (double*)w.r, (const double*)w.p, (const double*)w.ap, n, w.scalars, slot, ctx->red_partials, ctx->red_ticket);
+    else cg_update_xr_kernel<float><<<g, kCgThreads, 0, ctx->stream>>>((float*)x, (float*)w.r, (const float*)w.p, (const float*)w.ap, n, w.scalars, slot, ctx->red_partials, ctx->red_ticket);
     count_launch();
     SMB_CUDA(cudaGetLastError());
     return SMB200_OK;
@@ -259,7 +263,7 @@ smb200_status smb200_cg_solve(smb200_crs* a, const smb200_vec* b, smb200_vec* x,
     SMB_CUDA(cudaEventCreate(&ev1));
     SMB_CUDA(cudaEventRecord(ev0, ctx->stream));
 
-    double init[S_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double init[S_COUNT] = {0};
     init[S_THRESH] = threshold;
     memcpy(w.scalars_host + 3 * S_COUNT, init, sizeof init);
     SMB_CUDA(cudaMemcpyAsync(w.scalars, w.scalars_host + 3 * S_COUNT, sizeof init, cudaMemcpyHostToDevice, ctx->stream));

@@ -444,7 +444,7 @@ smb200_status smb200_dist_cg_solve(smb200_dist* d, const smb200_vec* b, smb200_v
     SMB_CUDA(cudaSetDevice(ctx->device));
     SMB_TRY(cg_prepare(ctx, w, d->vt, n, n + d->n_ghost, iter_max));
     double* S = w.scalars;
-    enum { S_RR = 0, S_PAP = 1, S_RR_NEW = 4, S_THRESH = 5, S_ITER = 6, S_DONE = 7, S_COUNT = 8 };
+    enum { S_RR = 0, S_PAP = 1, S_RR_NEW = 4, S_THRESH = 5, S_ITER = 6, S_DONE = 7, S_RR_LOCAL = 8, S_COUNT = 16 };   // cg.cu
 
     double threshold = tol;
     if (relative) {
@@ -456,14 +456,14 @@ smb200_status smb200_dist_cg_solve(smb200_dist* d, const smb200_vec* b, smb200_v
     SMB_CUDA(cudaEventCreate(&ev0));
     SMB_CUDA(cudaEventCreate(&ev1));
     SMB_CUDA(cudaEventRecord(ev0, ctx->stream));
-    double init[S_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double init[S_COUNT] = {0};
     init[S_THRESH] = threshold;
     memcpy(w.scalars_host + 3 * S_COUNT, init, sizeof init);
     SMB_CUDA(cudaMemcpyAsync(S, w.scalars_host + 3 * S_COUNT, sizeof init, cudaMemcpyHostToDevice, ctx->stream));
     // r = b - A x ; p = r ; rr = r.r
     SMB_TRY(dist_spmv_impl(d, x->d, w.ap, nullptr));
     SMB_TRY(cg_init_launch(ctx, w, d->vt, b->d, n));
-    if (multi) SMB_NCCL(g_nccl.AllReduce(S + S_RR_NEW, S + S_RR_NEW, 1, kNcclFloat64, kNcclSum, comm, ctx->stream));
+    if (multi) SMB_NCCL(g_nccl.AllReduce(S + S_RR_LOCAL, S + S_RR_NEW, 1, kNcclFloat64, kNcclSum, comm, ctx->stream));
 
     const int batch = 8;
     cudaEvent_t poll_ev[2];
@@ -485,7 +485,7 @@ smb200_status smb200_dist_cg_solve(smb200_dist* d, const smb200_vec* b, smb200_v
             st = dist_spmv_impl(d, w.p, w.ap, S);
             if (st == SMB200_OK && multi && g_nccl.AllReduce(S + S_PAP, S + S_PAP, 3, kNcclFloat64, kNcclSum, comm, ctx->stream) != 0) { set_error("dist_cg_solve: all-reduce failed"); st = SMB200_ERR_NCCL; }
             if (st == SMB200_OK) st = cg_xr_launch(ctx, w, d->vt, x->d, n);
-            if (st == SMB200_OK && multi && g_nccl.AllReduce(S + S_RR_NEW, S + S_RR_NEW, 1, kNcclFloat64, kNcclSum, comm, ctx->stream) != 0) { set_error("dist_cg_solve: all-reduce failed"); st = SMB200_ERR_NCCL; }
+            if (st == SMB200_OK && multi && g_nccl.AllReduce(S + S_RR_LOCAL, S + S_RR_NEW, 1, kNcclFloat64, kNcclSum, comm, ctx->stream) != 0) { set_error("dist_cg_solve: all-reduce failed"); st = SMB200_ERR_NCCL; }
             if (st == SMB200_OK) st = cg_p_launch(ctx, w, d->vt, n);
         }
         if (st != SMB200_OK) break;

@@ -1,0 +1,118 @@
+"""GPU, one process per GPU (needs >= 2 devices; skipped otherwise): the row-block distributed SpMV / dot / CG
+of libsmb200 (dist.cu, NCCL halo exchange + all-reduce) against the oracle's single-address-space results.
+Partition contract: sparsemat_par.rs:20-35 (contiguous row blocks, every block needs the x entries its columns touch)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import n_gpus
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out_q):
+    try:
+        sys.path.insert(0, ROOT)
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import torch.distributed as dist
+
+        import cases
+        import sparsemat_b200 as smb
+        from oracle import oracle_py as orc
+        dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+        ctx = smb.Context(rank)
+        box = [smb.Context.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, 0)
+        ctx.comm_init(rank, world, box[0])
+
+        # ---- (1) z-slab Laplacian generated on the device, halo planes exchanged over NCCL -------------------------
+        for vdt, tol in ((np.float64, 1e-12), (np.float32, 1e-5)):
+            nx, ny, nz = 24, 20, 4 * world + 3
+            n = nx * ny * nz
+            a = smb.DistCRS.laplace(ctx, vdt, np.uint32, nx, ny, nz)
+            d = a.dims()
+            lo, hi = d["row_lo"], d["row_lo"] + d["n_local"]
+            vals, cols, offs = orc.laplace(vdt, np.uint32, nx, ny, nz)
+            xg = orc.uniform(vdt, 4, n)
+            want = orc.mvp(vals, cols, offs, xg)
+            x = a.new_vec()
+            x.upload(xg[lo:hi])
+            y = a.mvp(x)
+            assert y.dim() == d["n_local"]
+            assert np.array_equal(y.to_numpy(), want[lo:hi]), "dist laplace spmv is not bit-exact"
+            # distributed dot (all-reduced) against the global sequential fold
+            got = a.dot(x, y)
+            ref = float(orc.dot(xg, want))
+            scale = float(np.sum(np.abs(xg.astype(np.float64) * want.astype(np.float64))))
+            assert abs(got - ref) <= max(tol, 0.5 * n * float(np.finfo(vdt).eps)) * scale, (got, ref)
+            # distributed CG: same iteration count (+-2%) and solution as the oracle's single-process solver
+            b_g = orc.mvp(vals, cols, offs, orc.uniform(vdt, 6, n))
+            b = a.new_vec()
+            b.upload(b_g[lo:hi])
+            xs = a.new_vec()
+            rtol = 1e-9 if vdt == np.float64 else 1e-4
+            st = smb.ConjugateGradient(rtol, 3000, relative=True).solve_with_stats(a, b, xs)
+            xo = np.zeros(n, vdt)
+            so = orc.cg(n, n, vals, cols, offs, b_g, xo, tol=rtol, relative=True, iter_max=3000)
+            assert st["converged"] and so["converged"], (st, so)
+            assert abs(int(st["iterations"]) - so["iterations"]) <= max(2, so["iterations"] // 50), (st, so["iterations"])
+            assert st["final_residual"] <= rtol * np.linalg.norm(b_g.astype(np.float64)) * 1.0000001
+            assert np.allclose(xs.to_numpy(), xo[lo:hi], rtol=0, atol=1e-7 if vdt == np.float64 else 2e-3)
+
+        # ---- (2) general matrix: host ghost plan, packed sends, nnz-balanced bounds ---------------------------------
+        vdt, idt = np.float64, np.uint64
+        n, _, vals, cols, offs = cases.ragged(31, 6000, 6000, 14, vdt, idt, empty_frac=0.1)
+        bounds = smb.partition_rows_by_nnz(offs, world)
+        lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+        o64 = offs.astype(np.int64)
+        a = smb.DistCRS.from_local_block(ctx, n, bounds, vals[o64[lo]:o64[hi]], cols[o64[lo]:o64[hi]],
+                                         (o64[lo:hi + 1] - o64[lo]).astype(idt))
+        xg = orc.uniform(vdt, 5, n)
+        want = orc.mvp(vals, cols, offs, xg)
+        x = a.new_vec()
+        x.upload(xg[lo:hi])
+        for _ in range(3):                                               # repeated exchanges reuse the plan
+            y = a.mvp(x)
+            assert np.array_equal(y.to_numpy(), want[lo:hi]), "dist general spmv is not bit-exact"
+        ctx.sync()
+        dist.barrier()
+        dist.destroy_process_group()
+        out_q.put((rank, "ok"))
+    except Exception as e:  # noqa: BLE001
+        import traceback
+        out_q.put((rank, "FAIL: " + repr(e) + "\n" + traceback.format_exc()))
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_row_block_distributed_spmv_dot_cg(world):
+    if n_gpus() < world:
+        pytest.skip(f"needs {world} GPUs, have {n_gpus()}")
+    import torch.multiprocessing as mp
+    ctxm = mp.get_context("spawn")
+    q = ctxm.Queue()
+    port = _free_port()
+    procs = [ctxm.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = []
+    try:
+        for _ in range(world):
+            results.append(q.get(timeout=600))
+    finally:
+        for p in procs:
+            p.join(timeout=30)
+            if p.is_alive():
+                p.kill()
+    assert len(results) == world and all(msg == "ok" for _, msg in results), results
