@@ -317,7 +317,7 @@ smb200_status smb200_cg_solve(smb200_crs* a, const smb200_vec* b, smb200_vec* x,
                 }
                 e = cudaGraphLaunch(w.graph, ctx->stream);
                 if (e != cudaSuccess) { set_error("cg_solve: graph launch failed: %s", cudaGetErrorString(e)); st = SMB200_ERR_CUDA; break; }
-                count_launch(3 * (uint64_t)batch);
+                count_launch(4 * (uint64_t)batch);   // SpMV+dot, dot finalize, x/r update, p update
             } else {
                 for (uint64_t k = 0; k < nb && st == SMB200_OK; ++k) st = cg_iteration(a, x->d);
                 if (st != SMB200_OK) break;

@@ -59,16 +59,29 @@ template <class T> __device__ __forceinline__ T warp_sum_t(T v) {
     return v;
 }
 
+// Fused dot epilogue of the SpMV kernels: every CTA leaves ONE f64 partial; spmv_dot_finalize_kernel (launched
+// right behind on the same stream) folds them in index order.  No ticket atomics and no __threadfence in the hot
+// kernel: with ~40k CTAs a single-address ticket costs more than a quarter of the product itself (measured).
 template <class T, int THREADS = kSpmvThreads>
 __device__ __forceinline__ void finish_dot(double acc, const DotArgs& d) {
     __shared__ double scratch[THREADS / 32 + 1];
     const double bsum = block_sum<THREADS>(acc, scratch);
-    double total;
-    if (grid_sum<THREADS>(bsum, d.partials, d.ticket, scratch, total))
-        if (threadIdx.x == 0) {
-            *d.result = (double)(T)total;
-            if (d.roll_dst) *d.roll_dst = *d.roll_src;
-        }
+    if (threadIdx.x == 0) d.partials[blockIdx.x] = bsum;
+}
+
+constexpr int kFinalizeThreads = 1024;
+__global__ void __launch_bounds__(kFinalizeThreads)
+spmv_dot_finalize_kernel(const double* __restrict__ partials, unsigned n, int is_f32, double* __restrict__ result,
+                         double* __restrict__ roll_dst, const double* __restrict__ roll_src, const double* __restrict__ done) {
+    __shared__ double scratch[kFinalizeThreads / 32 + 1];
+    if (done != nullptr && __ldcg(done) != 0.0) return;      // the SpMV CTAs left early: keep the previous values
+    double acc = 0.0;
+    for (unsigned i = threadIdx.x; i < n; i += kFinalizeThreads) acc += __ldcg(partials + i);
+    const double total = block_sum<kFinalizeThreads>(acc, scratch);
+    if (threadIdx.x == 0) {
+        *result = is_f32 ? (double)(float)total : total;
+        if (roll_dst) *roll_dst = *roll_src;
+    }
 }
 __device__ __forceinline__ bool solver_done(const DotArgs& d) { return d.done != nullptr && __ldcg(d.done) != 0.0; }
 
@@ -233,7 +246,7 @@ __device__ __forceinline__ double rows_direct(const T* __restrict__ vals, const 
 
 // ---- K3: stream kernel, register-staged 128-bit loads -----------------------------------------------
 template <class T, class I, bool DOT>
-__global__ void __launch_bounds__(kSpmvThreads)
+__global__ void __launch_bounds__(kSpmvThreads, sizeof(T) == 4 ? 8 : 6)
 spmv_stream_kernel(const T* __restrict__ vals, const I* __restrict__ cols, const I* __restrict__ offs,
                    const I* __restrict__ blk_rows, const I* __restrict__ blk_nnz, unsigned cap, const T* __restrict__ x,
                    T* __restrict__ y, DotArgs dot) {
@@ -242,22 +255,30 @@ spmv_stream_kernel(const T* __restrict__ vals, const I* __restrict__ cols, const
     __shared__ unsigned int s_long_count;
     __shared__ unsigned int s_long_rows[kLongCap];
     __shared__ double scratch[kSpmvThreads / 32 + 1];
-    if constexpr (DOT) { if (solver_done(dot)) return; }
     if (threadIdx.x == 0) s_long_count = 0;
-    // one round trip for the block's row range and element range (the plan stores offset_rows[blk_rows[k]])
+    // one round trip for the block's row range and element range (the plan stores offset_rows[blk_rows[k]]) and,
+    // inside a CG solve, for the solver's stop flag
     const uint64_t r0 = (uint64_t)__ldg(blk_rows + blockIdx.x), r1 = (uint64_t)__ldg(blk_rows + blockIdx.x + 1);
     const uint64_t n0 = (uint64_t)__ldg(blk_nnz + blockIdx.x), n1 = (uint64_t)__ldg(blk_nnz + blockIdx.x + 1);
+    double stop = 0.0;
+    if constexpr (DOT) { if (dot.done != nullptr) stop = __ldcg(dot.done); }
     const uint64_t a0 = n0 & ~(uint64_t)3;
+    if constexpr (DOT) { if (stop != 0.0) return; }
     double acc = 0.0;
     // Row offsets of the first two rows this thread will sum: requested before the stream loads, first touched
     // after the barrier, so their latency hides behind the whole product phase.
     constexpr int KP = 2;
     I pfa[KP], pfe[KP];
+    T pfw[KP];                          // fused dot: the weights of those rows, requested just as early
 #pragma unroll
     for (int j = 0; j < KP; ++j) {
         const uint64_t r = r0 + threadIdx.x + (uint64_t)j * kSpmvThreads;
         pfa[j] = pfe[j] = 0;
-        if (r < r1) { pfa[j] = __ldg(offs + r); pfe[j] = __ldg(offs + r + 1); }
+        pfw[j] = T(0);
+        if (r < r1) {
+            pfa[j] = __ldg(offs + r); pfe[j] = __ldg(offs + r + 1);
+            if constexpr (DOT) pfw[j] = __ldg((const T*)dot.w + r);
+        }
     }
     __syncthreads();
     if (n1 - a0 <= (uint64_t)cap) {
@@ -303,7 +324,7 @@ spmv_stream_kernel(const T* __restrict__ vals, const I* __restrict__ cols, const
                     T sum = T(0);
                     for (unsigned k = a; k < e; ++k) sum = add_rn(sum, prod[k]);
                     y[r] = sum;
-                    if constexpr (DOT) acc_fast += (double)mul_rn(__ldg((const T*)dot.w + r), sum);
+                    if constexpr (DOT) acc_fast += (double)mul_rn(pfw[j], sum);
                 } else {
                     all_short = false;
                 }
@@ -891,6 +912,8 @@ smb200_status plan_build(smb200_crs* m) {
 }
 
 // ---- launch ---------------------------------------------------------------------------------------------
+static thread_local unsigned g_last_pipe_grid = 0;   // CTAs of the most recent persistent launch (= its dot partials)
+
 template <class T, class I, bool DOT>
 static smb200_status launch_typed(smb200_crs* m, const SpmvPlan& p, uint64_t rb, uint64_t re, const void* x, void* y,
                                   const DotArgs& dot) {
@@ -943,6 +966,7 @@ static smb200_status launch_typed(smb200_crs* m, const SpmvPlan& p, uint64_t rb,
         SMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, TH, smem));                              \
         if (resident < 1) resident = 1;                                                                                  \
         if ((uint64_t)resident * ctx->sm_count < grid) grid = (uint64_t)resident * ctx->sm_count;                        \
+        g_last_pipe_grid = (unsigned)grid;                                                                               \
         kern<<<(unsigned)grid, TH, smem, st>>>(vals, cols, offs, (const I*)p.blk_rows, (const I*)p.blk_nnz, p.blk_flags, \
                                                (unsigned)p.n_blocks, sh.cap, (unsigned)stages, xx, yy, dot);            \
     } while (0)
@@ -965,6 +989,16 @@ static smb200_status launch_typed(smb200_crs* m, const SpmvPlan& p, uint64_t rb,
     }
     count_launch();
     SMB_CUDA(cudaGetLastError());
+    if constexpr (DOT) {
+        unsigned n_partials;
+        if (p.variant == SMB200_SPMV_SCALAR || p.variant == SMB200_SPMV_VECTOR) n_partials = (unsigned)(((re - rb) + (kSpmvThreads / p.lanes) - 1) / (kSpmvThreads / p.lanes));
+        else if (p.variant == SMB200_SPMV_STREAM_PIPE) n_partials = g_last_pipe_grid;
+        else n_partials = (unsigned)p.n_blocks;
+        spmv_dot_finalize_kernel<<<1, kFinalizeThreads, 0, st>>>(dot.partials, n_partials, sizeof(T) == 4 ? 1 : 0, dot.result,
+                                                               dot.roll_dst, dot.roll_src, dot.done);
+        count_launch();
+        SMB_CUDA(cudaGetLastError());
+    }
     return SMB200_OK;
 }
 
