@@ -68,6 +68,8 @@ struct smb200_ctx {
     // scratch for reductions: partial sums + ticket + result slots
     double* red_partials = nullptr;      // [red_cap]
     size_t red_cap = 0;
+    double* red_partials_aux = nullptr;  // [red_cap_aux] dot partials of launches on the side stream (dist boundary rows)
+    size_t red_cap_aux = 0;
     unsigned int* red_ticket = nullptr;  // zero between uses
     double* red_result = nullptr;        // device [8]
     double* red_result_host = nullptr;   // pinned [8]
@@ -152,6 +154,11 @@ struct smb200_crs {
 };
 
 namespace smb {
+
+// SpMV launches normally go to ctx->stream with ctx->red_partials; dist.cu redirects the boundary-row launches to
+// the side stream (behind the halo receive) with their own partials buffer.
+struct LaunchRedirect { cudaStream_t stream = nullptr; double* partials = nullptr; };
+extern thread_local LaunchRedirect g_redirect;
 
 // implemented across the .cu files
 void ctx_retain(smb200_ctx* ctx);

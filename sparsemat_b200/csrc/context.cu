@@ -5,6 +5,7 @@ namespace smb {
 
 static thread_local char g_err[1024] = "";
 thread_local uint64_t g_launches = 0;
+thread_local LaunchRedirect g_redirect;
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -88,7 +89,11 @@ smb200_status smb200_ctx_create(int32_t device, void* stream, smb200_ctx** out) 
         if (e != cudaSuccess) { delete c; SMB_CUDA(e); }
         c->own_stream = true;
     }
-    cudaError_t e = cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking);
+    // side stream at the highest priority: the few boundary CTAs of a distributed SpMV slip in between the
+    // interior kernel's waves instead of queueing behind them
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    cudaError_t e = cudaStreamCreateWithPriority(&c->aux_stream, cudaStreamNonBlocking, prio_hi);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_a, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_b, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMalloc(&c->red_ticket, 4 * sizeof(unsigned int));
@@ -124,6 +129,7 @@ void ctx_teardown(smb200_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->comm) smb200_comm_destroy(c);
     if (c->red_partials) cudaFree(c->red_partials);
+    if (c->red_partials_aux) cudaFree(c->red_partials_aux);
     if (c->red_ticket) cudaFree(c->red_ticket);
     if (c->red_result) cudaFree(c->red_result);
     if (c->red_result_host) cudaFreeHost(c->red_result_host);

@@ -146,7 +146,6 @@ static smb200_status dist_exchange_begin(smb200_dist* d, void* x) {
         }
     }
     SMB_NCCL(g_nccl.GroupEnd());
-    SMB_CUDA(cudaEventRecord(ctx->ev_b, ctx->aux_stream));
     return SMB200_OK;
 }
 
@@ -160,17 +159,38 @@ static smb200_status dist_exchange_end(smb200_dist* d) {
 // y = (A x)_local.  S == nullptr: plain product.  S != nullptr: CG kernel A with p.Ap partials in S.
 static smb200_status dist_spmv_impl(smb200_dist* d, void* x, void* y, double* S) {
     smb200_crs* m = d->local;
+    smb200_ctx* ctx = d->ctx;
+    const bool exchange = !(ctx->world == 1 || (d->n_ghost == 0 && d->total_send == 0));
     SMB_TRY(dist_exchange_begin(d, x));
+    // Boundary rows: queued on the (high-priority) side stream right behind the halo receive, so they run as soon
+    // as the ghosts have landed, in between the waves of the interior kernel, instead of after it.
+    if (exchange) {
+        if (S && ctx->red_cap_aux < d->plan_lo.n_blocks + d->plan_hi.n_blocks + 16) {
+            SMB_CUDA(cudaStreamSynchronize(ctx->aux_stream));
+            if (ctx->red_partials_aux) cudaFree(ctx->red_partials_aux);
+            ctx->red_partials_aux = nullptr;
+            ctx->red_cap_aux = 2 * (d->plan_lo.n_blocks + d->plan_hi.n_blocks) + 1024;
+            SMB_CUDA(cudaMalloc(&ctx->red_partials_aux, ctx->red_cap_aux * sizeof(double)));
+        }
+        g_redirect.stream = ctx->aux_stream;
+        g_redirect.partials = S ? ctx->red_partials_aux : nullptr;
+    }
+    smb200_status st = SMB200_OK;
+    if (S) {
+        // rr <- rr_new is rolled once per product: by the interior launch, or by a boundary one if there is no interior
+        const bool no_int = d->int_end == d->int_begin;
+        st = spmv_launch_cg(m, d->plan_lo, 0, d->int_begin, x, y, x, S, 1, no_int);
+        if (st == SMB200_OK) st = spmv_launch_cg(m, d->plan_hi, d->int_end, d->n_local, x, y, x, S, 2, no_int && d->int_begin == 0);
+    } else {
+        st = spmv_launch_plan(m, d->plan_lo, 0, d->int_begin, x, y, nullptr, 0);
+        if (st == SMB200_OK) st = spmv_launch_plan(m, d->plan_hi, d->int_end, d->n_local, x, y, nullptr, 0);
+    }
+    g_redirect = LaunchRedirect();
+    SMB_TRY(st);
+    if (exchange) SMB_CUDA(cudaEventRecord(ctx->ev_b, ctx->aux_stream));
     if (S) SMB_TRY(spmv_launch_cg(m, d->plan_int, d->int_begin, d->int_end, x, y, x, S, 0, true));
     else SMB_TRY(spmv_launch_plan(m, d->plan_int, d->int_begin, d->int_end, x, y, nullptr, 0));
     SMB_TRY(dist_exchange_end(d));
-    if (S) {
-        SMB_TRY(spmv_launch_cg(m, d->plan_lo, 0, d->int_begin, x, y, x, S, 1, d->int_end == d->int_begin));
-        SMB_TRY(spmv_launch_cg(m, d->plan_hi, d->int_end, d->n_local, x, y, x, S, 2, d->int_end == d->int_begin && d->int_begin == 0));
-    } else {
-        SMB_TRY(spmv_launch_plan(m, d->plan_lo, 0, d->int_begin, x, y, nullptr, 0));
-        SMB_TRY(spmv_launch_plan(m, d->plan_hi, d->int_end, d->n_local, x, y, nullptr, 0));
-    }
     return SMB200_OK;
 }
 

@@ -923,7 +923,7 @@ static smb200_status launch_typed(smb200_crs* m, const SpmvPlan& p, uint64_t rb,
     const I* offs = (const I*)m->offsets;
     const T* xx = (const T*)x;
     T* yy = (T*)y;
-    cudaStream_t st = ctx->stream;
+    cudaStream_t st = g_redirect.stream ? g_redirect.stream : ctx->stream;
     if (p.variant == SMB200_SPMV_SCALAR || p.variant == SMB200_SPMV_VECTOR) {
         const uint64_t rows = re - rb;
         const int rows_per_cta = kSpmvThreads / p.lanes;
@@ -1038,8 +1038,15 @@ static smb200_status spmv_launch_impl(smb200_crs* m, const SpmvPlan& p, uint64_t
     DotArgs dot{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     if (w) {
         uint64_t blocks = p.variant >= SMB200_SPMV_STREAM ? p.n_blocks : ((re - rb) * (uint64_t)p.lanes + kSpmvThreads - 1) / kSpmvThreads;
-        SMB_TRY(ensure_reduction_scratch(ctx, blocks));
-        dot = DotArgs{w, ctx->red_partials, ctx->red_ticket, result, roll_dst, roll_src, done};
+        double* partials = ctx->red_partials;
+        if (g_redirect.partials) {
+            SMB_REQUIRE(blocks <= ctx->red_cap_aux, SMB200_ERR_INVALID, "spmv: side-stream partials buffer too small");
+            partials = g_redirect.partials;
+        } else {
+            SMB_TRY(ensure_reduction_scratch(ctx, blocks));
+            partials = ctx->red_partials;
+        }
+        dot = DotArgs{w, partials, ctx->red_ticket, result, roll_dst, roll_src, done};
     }
     static thread_local const void* window_on = nullptr;
     if (p.flags & SMB200_FLAG_L2_PERSIST_X) {
