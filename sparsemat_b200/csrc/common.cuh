@@ -62,6 +62,7 @@ struct smb200_ctx {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     cudaStream_t aux_stream = nullptr;   // halo traffic / overlap
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;   // smb200_spmv_host: H2D / D2H run beside the compute stream
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     int sm_count = 0;
     size_t l2_bytes = 0, l2_persist_max = 0;
@@ -119,6 +120,18 @@ struct SpmvPlan {
     bool built = false;
 };
 
+// Host-buffer pipeline of smb200_spmv_host: the rows are cut into chunks; chunk c starts as soon as the pieces of x its
+// columns reach have arrived (banded matrices: a few pieces), and its slice of y goes back while later chunks compute.
+struct HostPipe {
+    bool built = false;
+    int n_chunks = 0;
+    std::vector<uint64_t> row_bounds;    // [n_chunks + 1]
+    std::vector<uint64_t> x_bounds;      // [n_chunks + 1] pieces of x (elements)
+    std::vector<int> last_piece;         // per chunk: the last piece of x it reads
+    std::vector<SpmvPlan> plans;         // per chunk
+    std::vector<cudaEvent_t> ev_x, ev_y;
+};
+
 // CG workspace kept with the matrix so repeated solves do not reallocate.
 struct CgWork {
     uint64_t n = 0;
@@ -150,6 +163,7 @@ struct smb200_crs {
     uint32_t want_flags = 0;
     smb::SpmvPlan plan;
     smb::CgWork cg;
+    smb::HostPipe hp;
     uint64_t x_extra = 0;               // dist: number of ghost entries appended to x (n_cols counts them)
 };
 
@@ -172,6 +186,7 @@ smb200_status plan_build(smb200_crs* m);
 smb200_status plan_build_range(smb200_crs* m, SpmvPlan& p, int want_variant, int want_lanes, uint32_t flags,
                                uint64_t row_begin, uint64_t row_end);
 void plan_free(SpmvPlan& p);
+void hostpipe_free(HostPipe& hp);
 void cg_free(CgWork& w);
 smb200_status spmv_launch_plan(smb200_crs* m, const SpmvPlan& p, uint64_t row_begin, uint64_t row_end, const void* x,
                                void* y, const void* w, int dot_slot);

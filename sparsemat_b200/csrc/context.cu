@@ -139,6 +139,8 @@ void ctx_teardown(smb200_ctx* c) {
     if (c->ev_a) cudaEventDestroy(c->ev_a);
     if (c->ev_b) cudaEventDestroy(c->ev_b);
     if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
+    if (c->copy_in) cudaStreamDestroy(c->copy_in);
+    if (c->copy_out) cudaStreamDestroy(c->copy_out);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }

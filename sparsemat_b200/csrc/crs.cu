@@ -181,6 +181,7 @@ smb200_status crs_alloc(smb200_ctx* ctx, int vt, int it, uint64_t n_rows, uint64
 smb200_status crs_finalize(smb200_crs* m, bool validate) {
     smb200_ctx* ctx = m->ctx;
     plan_free(m->plan);
+    hostpipe_free(m->hp);
     m->max_row_len = 0;
     if (m->n_rows == 0) return SMB200_OK;
     CrsCheck* dchk = nullptr;
@@ -351,6 +352,7 @@ smb200_status smb200_crs_free(smb200_crs* m) {
     cudaSetDevice(m->ctx->device);
     cudaStreamSynchronize(m->ctx->stream);
     plan_free(m->plan);
+    hostpipe_free(m->hp);
     cg_free(m->cg);
     if (m->values) cudaFree(m->values);
     if (m->columns) cudaFree(m->columns);

@@ -757,6 +757,33 @@ block_window_kernel(const I* __restrict__ cols, const I* __restrict__ offs, cons
     }
 }
 
+void hostpipe_free(HostPipe& hp) {
+    for (auto& p : hp.plans) plan_free(p);
+    for (auto e : hp.ev_x) cudaEventDestroy(e);
+    for (auto e : hp.ev_y) cudaEventDestroy(e);
+    hp = HostPipe();
+}
+
+// [min column, max column + 1) over the elements of rows [r_lo, r_hi): which pieces of x a chunk needs
+template <class I>
+__global__ void col_range_kernel(const I* __restrict__ cols, const I* __restrict__ offs, uint64_t r_lo, uint64_t r_hi,
+                                 unsigned long long* __restrict__ out2) {
+    const uint64_t n0 = (uint64_t)offs[r_lo], n1 = (uint64_t)offs[r_hi];
+    unsigned long long mn = ~0ull, mx = 0ull;
+    for (uint64_t k = n0 + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; k < n1; k += (uint64_t)gridDim.x * blockDim.x) {
+        const unsigned long long c = (unsigned long long)cols[k];
+        mn = c < mn ? c : mn;
+        mx = c + 1 > mx ? c + 1 : mx;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long a = __shfl_xor_sync(0xffffffffu, mn, o), b = __shfl_xor_sync(0xffffffffu, mx, o);
+        mn = a < mn ? a : mn;
+        mx = b > mx ? b : mx;
+    }
+    if ((threadIdx.x & 31) == 0) { atomicMin(out2, mn); atomicMax(out2 + 1, mx); }
+}
+
 void plan_free(SpmvPlan& p) {
     if (p.blk_rows) cudaFree(p.blk_rows);
     if (p.blk_nnz) cudaFree(p.blk_nnz);
@@ -830,6 +857,10 @@ smb200_status plan_build_range(smb200_crs* m, SpmvPlan& p, int want_variant, int
         // Row-length statistics decide: short/medium rows -> stream (balanced, bit-exact row sums);
         // long regular rows -> a warp per row reads them with full coalescing and no staging.
         variant = (mean >= 96.0 && m->max_row_len < 8 * (uint64_t)mean + 4096) ? SMB200_SPMV_VECTOR : SMB200_SPMV_STREAM;
+        // small short-row matrices that live in L2 (config C1): nothing to stream from HBM, the two-phase stream
+        // kernel only adds latency; one thread per row wins there (12.4 us vs 18.4 us warm on the 1024^2 Laplacian)
+        const uint64_t bytes = m->nnz * (vsize(m->vt) + isize(m->it)) + (m->n_rows + 1) * isize(m->it) + (m->n_cols + m->n_rows) * vsize(m->vt);
+        if (bytes * 3 < (uint64_t)ctx->l2_bytes * 2 && m->max_row_len <= 16) variant = SMB200_SPMV_SCALAR;
     }
     p.variant = variant;
     p.lanes = 0;
@@ -1093,6 +1124,7 @@ smb200_status smb200_crs_configure(smb200_crs* m, smb200_spmv_variant variant, i
     m->want_flags = flags;
     cudaStreamSynchronize(m->ctx->stream);
     plan_free(m->plan);
+    hostpipe_free(m->hp);
     if (m->n_rows == 0) return SMB200_OK;
     return plan_build(m);
 }
@@ -1148,9 +1180,83 @@ smb200_status smb200_spmv_host(smb200_crs* a, const void* x_host, uint64_t nx, v
         SMB_TRY(dev_alloc(&ctx->stage_y, yb));
         ctx->stage_y_bytes = yb;
     }
-    if (xb) SMB_CUDA(cudaMemcpyAsync(ctx->stage_x, x_host, xb, cudaMemcpyHostToDevice, ctx->stream));
-    SMB_TRY(spmv_launch(a, ctx->stage_x, ctx->stage_y, nullptr, 0));
-    if (yb) SMB_CUDA(cudaMemcpyAsync(y_host, ctx->stage_y, yb, cudaMemcpyDeviceToHost, ctx->stream));
+    if (a->n_rows == 0) return SMB200_OK;
+    // ---- pipelined path: H2D pieces of x | row chunks | D2H slices of y on three streams ---------------------------
+    HostPipe& hp = a->hp;
+    if (!hp.built) {
+        int chunks = env_int("SMB200_HOST_CHUNKS", 0);
+        if (chunks <= 0) chunks = (int)((a->n_rows + 524287) / 524288);
+        if (chunks > 64) chunks = 64;
+        if (chunks < 1 || env_int("SMB200_HOST_PIPE", 1) == 0) chunks = 1;
+        hp.n_chunks = chunks;
+        hp.row_bounds.assign(chunks + 1, a->n_rows);
+        hp.x_bounds.assign(chunks + 1, a->n_cols);
+        for (int c = 0; c < chunks; ++c) {
+            hp.row_bounds[c] = ((a->n_rows * (uint64_t)c / (uint64_t)chunks) + 1023) / 1024 * 1024;
+            hp.x_bounds[c] = ((a->n_cols * (uint64_t)c / (uint64_t)chunks) + 1023) / 1024 * 1024;
+            if (hp.row_bounds[c] > a->n_rows) hp.row_bounds[c] = a->n_rows;
+            if (hp.x_bounds[c] > a->n_cols) hp.x_bounds[c] = a->n_cols;
+        }
+        hp.row_bounds[0] = 0; hp.x_bounds[0] = 0;
+        hp.last_piece.assign(chunks, chunks - 1);
+        hp.plans.resize(chunks);
+        if (chunks > 1) {
+            if (!ctx->copy_in) SMB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
+            if (!ctx->copy_out) SMB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
+            unsigned long long* d_rng = nullptr;
+            std::vector<unsigned long long> h_rng(2 * (size_t)chunks);
+            SMB_CUDA(cudaMalloc(&d_rng, h_rng.size() * sizeof(unsigned long long)));
+            for (int c = 0; c < chunks; ++c) { h_rng[2 * c] = ~0ull; h_rng[2 * c + 1] = 0ull; }
+            SMB_CUDA(cudaMemcpyAsync(d_rng, h_rng.data(), h_rng.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
+            for (int c = 0; c < chunks; ++c) {
+                if (hp.row_bounds[c + 1] <= hp.row_bounds[c] || a->nnz == 0) continue;
+                if (a->it == SMB200_U64) col_range_kernel<uint64_t><<<ctx->sm_count, 256, 0, ctx->stream>>>((const uint64_t*)a->columns, (const uint64_t*)a->offsets, hp.row_bounds[c], hp.row_bounds[c + 1], d_rng + 2 * c);
+                else col_range_kernel<uint32_t><<<ctx->sm_count, 256, 0, ctx->stream>>>((const uint32_t*)a->columns, (const uint32_t*)a->offsets, hp.row_bounds[c], hp.row_bounds[c + 1], d_rng + 2 * c);
+                count_launch();
+            }
+            cudaError_t e = cudaMemcpyAsync(h_rng.data(), d_rng, h_rng.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+            cudaFree(d_rng);
+            SMB_CUDA(e);
+            for (int c = 0; c < chunks; ++c) {
+                const unsigned long long mx = h_rng[2 * c + 1];           // max column + 1 (0: the chunk has no entries)
+                int piece = 0;
+                while (piece + 1 < chunks && hp.x_bounds[piece + 1] < mx) ++piece;
+                hp.last_piece[c] = mx ? piece : 0;
+            }
+            // a chunk may start only when everything up to its last piece is in: make that monotone in c
+            for (int c = 1; c < chunks; ++c) if (hp.last_piece[c] < hp.last_piece[c - 1]) hp.last_piece[c] = hp.last_piece[c - 1];
+            hp.ev_x.resize(chunks); hp.ev_y.resize(chunks);
+            for (int c = 0; c < chunks; ++c) {
+                SMB_CUDA(cudaEventCreateWithFlags(&hp.ev_x[c], cudaEventDisableTiming));
+                SMB_CUDA(cudaEventCreateWithFlags(&hp.ev_y[c], cudaEventDisableTiming));
+                SMB_TRY(plan_build_range(a, hp.plans[c], a->want_variant, a->want_lanes, a->want_flags, hp.row_bounds[c], hp.row_bounds[c + 1]));
+            }
+        }
+        hp.built = true;
+    }
+    if (hp.n_chunks <= 1) {
+        if (xb) SMB_CUDA(cudaMemcpyAsync(ctx->stage_x, x_host, xb, cudaMemcpyHostToDevice, ctx->stream));
+        SMB_TRY(spmv_launch(a, ctx->stage_x, ctx->stage_y, nullptr, 0));
+        if (yb) SMB_CUDA(cudaMemcpyAsync(y_host, ctx->stage_y, yb, cudaMemcpyDeviceToHost, ctx->stream));
+        SMB_CUDA(cudaStreamSynchronize(ctx->stream));
+        return SMB200_OK;
+    }
+    for (int k = 0; k < hp.n_chunks; ++k) {
+        const size_t lo = (size_t)hp.x_bounds[k] * es, hi = (size_t)hp.x_bounds[k + 1] * es;
+        if (hi > lo) SMB_CUDA(cudaMemcpyAsync((char*)ctx->stage_x + lo, (const char*)x_host + lo, hi - lo, cudaMemcpyHostToDevice, ctx->copy_in));
+        SMB_CUDA(cudaEventRecord(hp.ev_x[k], ctx->copy_in));
+    }
+    int waited = -1;
+    for (int c = 0; c < hp.n_chunks; ++c) {
+        const uint64_t rb = hp.row_bounds[c], re = hp.row_bounds[c + 1];
+        if (hp.last_piece[c] > waited) { SMB_CUDA(cudaStreamWaitEvent(ctx->stream, hp.ev_x[hp.last_piece[c]], 0)); waited = hp.last_piece[c]; }
+        if (re > rb) SMB_TRY(spmv_launch_plan(a, hp.plans[c], rb, re, ctx->stage_x, ctx->stage_y, nullptr, 0));
+        SMB_CUDA(cudaEventRecord(hp.ev_y[c], ctx->stream));
+        SMB_CUDA(cudaStreamWaitEvent(ctx->copy_out, hp.ev_y[c], 0));
+        if (re > rb) SMB_CUDA(cudaMemcpyAsync((char*)y_host + (size_t)rb * es, (const char*)ctx->stage_y + (size_t)rb * es, (size_t)(re - rb) * es, cudaMemcpyDeviceToHost, ctx->copy_out));
+    }
+    SMB_CUDA(cudaStreamSynchronize(ctx->copy_out));
     SMB_CUDA(cudaStreamSynchronize(ctx->stream));
     return SMB200_OK;
 }

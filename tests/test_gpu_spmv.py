@@ -96,6 +96,28 @@ def test_edge_shapes(smb, orc, ctx, vdt, idt):
     assert a.mvp(smb.DenseVec(ctx, 0, vdt)).dim() == 0
 
 
+@pytest.mark.parametrize("chunks", ["3", "7"])
+def test_host_buffer_pipeline_chunks(smb, orc, ctx, chunks, monkeypatch):
+    """smb200_spmv_host cuts the rows into chunks (H2D pieces of x | compute | D2H slices of y overlap); forced here on
+    small matrices: banded (a chunk waits for a few pieces of x), unstructured (waits for all of x), ragged ends."""
+    monkeypatch.setenv("SMB200_HOST_CHUNKS", chunks)
+    for case in (cases.banded(12, 9000, 300, 7, F32, U32), cases.ragged(13, 5000, 7000, 25, F64, U64),
+                 cases.powerlaw(14, 4000, 4000, 3000, F64, U32), cases.all_empty(2500, 10, F32, U32)):
+        n_rows, n_cols, vals, cols, offs = case
+        x = np.random.default_rng(3).uniform(-1, 1, n_cols).astype(vals.dtype)
+        a = smb.SparseMatCRS.from_raw_parts(ctx, n_rows, n_cols, vals, cols, offs)
+        want = a.mvp(smb.DenseVec.from_vec(ctx, x)).to_numpy()
+        hx, hy = smb.pinned_empty(n_cols, vals.dtype), smb.pinned_empty(n_rows, vals.dtype)
+        hx[:] = x
+        for _ in range(2):
+            hy[:] = -7.0
+            a.mvp_host(hx, hy)
+            assert np.array_equal(hy, want)
+        assert np.array_equal(a.mvp_host(x), want)                            # pageable host memory works too
+        a.configure(smb.SPMV_SCALAR)                                          # re-planning rebuilds the chunk plans
+        assert np.array_equal(a.mvp_host(hx, hy), orc.mvp(vals, cols, offs, x))
+
+
 def test_reference_known_answers(smb, ctx):
     """lib.rs:80-82 (34.544, storage order [col1, col2, col0]) and lib.rs:150-152 (20.16), f32, assert_eq!."""
     a = smb.SparseMatCRS.from_raw_parts(ctx, 3, 3, np.array([4.2, 0.12, 7.12, 4.12, 2.24, 2.12], F32),
