@@ -182,7 +182,7 @@ def run_reference(args):
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gflops": base["gflops"], "wall_s": time.perf_counter() - t0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -337,6 +337,7 @@ def run_ours(args):
         xs.fill_uniform(6)
         b = a64.mvp(xs)
         x0 = smb.DenseVec(ctx, n_local, np.float64)
+        smb.ConjugateGradient(1e-30, 17).solve_with_stats(a64, b, smb.DenseVec(ctx, n_local, np.float64))   # untimed: graph capture
         st = smb.ConjugateGradient(1e-8, 5000, relative=True).solve_with_stats(a64, b, x0)
         Bcg = algorithmic_bytes(n_local, n_local, nnz_local, 8, 4) + 9 * n_local * 8
         its = max(1, int(st["iterations"]))
@@ -346,20 +347,60 @@ def run_ours(args):
                       "effective_gbs": Bcg * its / (st["device_ms"] * 1e-3) / 1e9,
                       "frac_of_measured_hbm_peak": Bcg * its / (st["device_ms"] * 1e-3) / 1e9 / peak,
                       "launches": int(st["launches"])}
+    if multi and not args.no_cg:
+        # CG iter/s at N GPUs (BASELINE.json metric): weak scaling, every rank a 256^3 f64/u32 slab; fixed iteration count
+        del a, x, y
+        a64 = smb.DistCRS.laplace(ctx, np.float64, idt, NX, NY, NZ_PER_GPU * world)
+        xs = a64.new_vec()
+        xs.fill_uniform(6 + rank)
+        b = a64.mvp(xs)
+        x0 = a64.new_vec()
+        cg_iters = 200
+        # one short untimed solve first: NCCL connects its all-reduce channels lazily and the iteration graph is captured once
+        smb.ConjugateGradient(1e-30, 17).solve_with_stats(a64, b, a64.new_vec())
+        barrier()
+        st = smb.ConjugateGradient(1e-30, cg_iters).solve_with_stats(a64, b, x0)
+        tms = torch.tensor([st["device_ms"]], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        Bcg = (algorithmic_bytes(n_local, n_local, a64.dims()["nnz_local"], 8, 4) + 9 * n_local * 8) * world
+        line["cg"] = {"workload": f"{cg_iters} CG iterations on the 256x256x{NZ_PER_GPU * world} f64/u32 Laplacian, z-slab row blocks "
+                                  "(BASELINE.json configs[3] per GPU, weak scaling)",
+                      "iterations": int(st["iterations"]), "device_ms": float(tms.item()),
+                      "iter_per_s": int(st["iterations"]) / (float(tms.item()) * 1e-3),
+                      "effective_gbs": Bcg * int(st["iterations"]) / (float(tms.item()) * 1e-3) / 1e9,
+                      "frac_of_measured_hbm_peak": Bcg * int(st["iterations"]) / (float(tms.item()) * 1e-3) / 1e9 / (peak * world)}
     if not multi and not args.no_cpu:
         base, _ = cpu_reference(5, 1, want_cg=not args.no_cg)
         line["cpu_baseline"] = base
     elif rank == 0:
         line["cpu_baseline"] = None if multi else {"skipped": "--no-cpu"}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if multi:
         dist.barrier()
         dist.destroy_process_group()
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The ONE JSON line goes to the process's original stdout; everything else (NCCL banners, warnings) was
+    diverted to stderr in main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)                       # libraries that print to fd 1 (e.g. "NCCL version ...") land on stderr
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=500)

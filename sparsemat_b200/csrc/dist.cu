@@ -15,6 +15,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 namespace smb {
 
@@ -164,6 +165,21 @@ static smb200_status dist_spmv_impl(smb200_dist* d, void* x, void* y, double* S)
     SMB_TRY(dist_exchange_begin(d, x));
     // Boundary rows: queued on the (high-priority) side stream right behind the halo receive, so they run as soon
     // as the ghosts have landed, in between the waves of the interior kernel, instead of after it.
+    static const bool overlap = []{ const char* e = getenv("SMB200_DIST_OVERLAP"); return !(e && e[0] == '0'); }();
+    if (exchange && !overlap) {                 // debugging aid: boundary rows on the main stream after the interior
+        SMB_CUDA(cudaEventRecord(ctx->ev_b, ctx->aux_stream));
+        if (S) SMB_TRY(spmv_launch_cg(m, d->plan_int, d->int_begin, d->int_end, x, y, x, S, 0, true));
+        else SMB_TRY(spmv_launch_plan(m, d->plan_int, d->int_begin, d->int_end, x, y, nullptr, 0));
+        SMB_TRY(dist_exchange_end(d));
+        if (S) {
+            SMB_TRY(spmv_launch_cg(m, d->plan_lo, 0, d->int_begin, x, y, x, S, 1, d->int_end == d->int_begin));
+            SMB_TRY(spmv_launch_cg(m, d->plan_hi, d->int_end, d->n_local, x, y, x, S, 2, d->int_end == d->int_begin && d->int_begin == 0));
+        } else {
+            SMB_TRY(spmv_launch_plan(m, d->plan_lo, 0, d->int_begin, x, y, nullptr, 0));
+            SMB_TRY(spmv_launch_plan(m, d->plan_hi, d->int_end, d->n_local, x, y, nullptr, 0));
+        }
+        return SMB200_OK;
+    }
     if (exchange) {
         if (S && ctx->red_cap_aux < d->plan_lo.n_blocks + d->plan_hi.n_blocks + 16) {
             SMB_CUDA(cudaStreamSynchronize(ctx->aux_stream));
@@ -485,28 +501,58 @@ smb200_status smb200_dist_cg_solve(smb200_dist* d, const smb200_vec* b, smb200_v
     SMB_TRY(cg_init_launch(ctx, w, d->vt, b->d, n));
     if (multi) SMB_NCCL(g_nccl.AllReduce(S + S_RR_LOCAL, S + S_RR_NEW, 1, kNcclFloat64, kNcclSum, comm, ctx->stream));
 
-    const int batch = 8;
+    const char* benv = getenv("SMB200_CG_BATCH");
+    int batch = benv ? atoi(benv) : 8;
+    if (batch < 1) batch = 1;
+    const char* genv = getenv("SMB200_CG_GRAPH");
+    const bool use_graph = !(genv && genv[0] == '0');
     cudaEvent_t poll_ev[2];
     SMB_CUDA(cudaEventCreateWithFlags(&poll_ev[0], cudaEventDisableTiming));
     SMB_CUDA(cudaEventCreateWithFlags(&poll_ev[1], cudaEventDisableTiming));
     smb200_status st = SMB200_OK;
     uint64_t launched = 0, rounds = 0;
     bool finished = false;
+    // One iteration: halo exchange + SpMV with p.Ap fused (three launches) | all-reduce | x, r update + r.r | all-reduce | p update.
+    // Every rank runs the same sequence: the stop flag derives from all-reduced values, hence is identical everywhere, and
+    // iterations past it exit early on the device.
+    auto iteration = [&]() -> smb200_status {
+        if (multi && cudaMemsetAsync(S + S_PAP, 0, 3 * sizeof(double), ctx->stream) != cudaSuccess) { set_error("dist_cg_solve: memset failed"); return SMB200_ERR_CUDA; }
+        SMB_TRY(dist_spmv_impl(d, w.p, w.ap, S));
+        if (multi && g_nccl.AllReduce(S + S_PAP, S + S_PAP, 3, kNcclFloat64, kNcclSum, comm, ctx->stream) != 0) { set_error("dist_cg_solve: all-reduce failed"); return SMB200_ERR_NCCL; }
+        SMB_TRY(cg_xr_launch(ctx, w, d->vt, x->d, n));
+        if (multi && g_nccl.AllReduce(S + S_RR_LOCAL, S + S_RR_NEW, 1, kNcclFloat64, kNcclSum, comm, ctx->stream) != 0) { set_error("dist_cg_solve: all-reduce failed"); return SMB200_ERR_NCCL; }
+        return cg_p_launch(ctx, w, d->vt, n);
+    };
+    // the first iteration runs eagerly: it performs every lazy allocation / connection set-up outside of stream capture
+    if (iter_max > 0) { st = iteration(); launched = 1; }
     while (st == SMB200_OK && !finished) {
         const int slot = (int)(rounds & 1);
         cudaError_t e = cudaMemcpyAsync(w.scalars_host + slot * S_COUNT, S, S_COUNT * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
         if (e == cudaSuccess) e = cudaEventRecord(poll_ev[slot], ctx->stream);
         if (e != cudaSuccess) { set_error("dist_cg_solve: %s", cudaGetErrorString(e)); st = SMB200_ERR_CUDA; break; }
         const uint64_t nb = std::min<uint64_t>(iter_max - launched, (uint64_t)batch);
-        for (uint64_t k = 0; k < nb && st == SMB200_OK; ++k) {
-            // every rank runs the same number of launches: the stop flag is derived from all-reduced
-            // values, hence identical everywhere, and finished iterations exit early on the device
-            if (multi && cudaMemsetAsync(S + S_PAP, 0, 3 * sizeof(double), ctx->stream) != cudaSuccess) { set_error("dist_cg_solve: memset failed"); st = SMB200_ERR_CUDA; break; }
-            st = dist_spmv_impl(d, w.p, w.ap, S);
-            if (st == SMB200_OK && multi && g_nccl.AllReduce(S + S_PAP, S + S_PAP, 3, kNcclFloat64, kNcclSum, comm, ctx->stream) != 0) { set_error("dist_cg_solve: all-reduce failed"); st = SMB200_ERR_NCCL; }
-            if (st == SMB200_OK) st = cg_xr_launch(ctx, w, d->vt, x->d, n);
-            if (st == SMB200_OK && multi && g_nccl.AllReduce(S + S_RR_LOCAL, S + S_RR_NEW, 1, kNcclFloat64, kNcclSum, comm, ctx->stream) != 0) { set_error("dist_cg_solve: all-reduce failed"); st = SMB200_ERR_NCCL; }
-            if (st == SMB200_OK) st = cg_p_launch(ctx, w, d->vt, n);
+        if (nb == (uint64_t)batch && use_graph) {
+            // a batch of iterations — kernels, NCCL send/recv and all-reduces on both streams — replayed from one CUDA graph,
+            // so the host enqueues one node per batch instead of ~20 calls per iteration
+            if (!w.graph || w.graph_batch != batch || w.graph_x != x->d || w.graph_partials != ctx->red_partials || w.graph_plan != (const void*)d) {
+                if (w.graph) { cudaGraphExecDestroy(w.graph); w.graph = nullptr; }
+                cudaGraph_t graph = nullptr;
+                e = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal);
+                if (e == cudaSuccess) {
+                    for (int k = 0; k < batch && st == SMB200_OK; ++k) st = iteration();
+                    cudaError_t e2 = cudaStreamEndCapture(ctx->stream, &graph);
+                    if (st == SMB200_OK && e2 != cudaSuccess) e = e2;
+                }
+                if (st == SMB200_OK && e == cudaSuccess) e = cudaGraphInstantiate(&w.graph, graph, 0);
+                if (graph) cudaGraphDestroy(graph);
+                if (e != cudaSuccess && st == SMB200_OK) { set_error("dist_cg_solve: graph capture failed: %s", cudaGetErrorString(e)); st = SMB200_ERR_CUDA; }
+                if (st != SMB200_OK) break;
+                w.graph_batch = batch; w.graph_x = x->d; w.graph_partials = ctx->red_partials; w.graph_plan = (const void*)d;
+            }
+            e = cudaGraphLaunch(w.graph, ctx->stream);
+            if (e != cudaSuccess) { set_error("dist_cg_solve: graph launch failed: %s", cudaGetErrorString(e)); st = SMB200_ERR_CUDA; break; }
+        } else {
+            for (uint64_t k = 0; k < nb && st == SMB200_OK; ++k) st = iteration();
         }
         if (st != SMB200_OK) break;
         launched += nb;
