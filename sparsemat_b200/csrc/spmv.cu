@@ -972,7 +972,7 @@ static smb200_status launch_typed(smb200_crs* m, const SpmvPlan& p, uint64_t rb,
         if (p.variant == SMB200_SPMV_STREAM) {
             const size_t smem = (size_t)(sh.cap + 8) * sizeof(T);
             auto kern = spmv_stream_kernel<T, I, DOT>;
-            if (smem > 48 * 1024) SMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (smem > 32 * 1024) SMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             if (carve >= 0) SMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
             kern<<<(unsigned)p.n_blocks, kSpmvThreads, smem, st>>>(vals, cols, offs, (const I*)p.blk_rows, (const I*)p.blk_nnz, sh.cap, xx, yy, dot);
         } else if (p.variant == SMB200_SPMV_STREAM_PIPE) {
@@ -1007,13 +1007,13 @@ static smb200_status launch_typed(smb200_crs* m, const SpmvPlan& p, uint64_t rb,
         } else if (p.variant == SMB200_SPMV_STREAM_TMA) {
             const size_t smem = (size_t)sh.cap * (sizeof(T) + sizeof(I));
             auto kern = spmv_stream_tma_kernel<T, I, DOT, false>;
-            if (smem > 48 * 1024) SMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (smem > 32 * 1024) SMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             if (carve >= 0) SMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
             kern<<<(unsigned)p.n_blocks, kSpmvThreads, smem, st>>>(vals, cols, offs, (const I*)p.blk_rows, nullptr, sh.cap, 0u, xx, yy, dot);
         } else {
             const size_t smem = (size_t)sh.cap * (sizeof(T) + sizeof(I)) + (size_t)sh.win_cap * sizeof(T);
             auto kern = spmv_stream_tma_kernel<T, I, DOT, true>;
-            if (smem > 48 * 1024) SMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (smem > 32 * 1024) SMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             if (carve >= 0) SMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
             kern<<<(unsigned)p.n_blocks, kSpmvThreads, smem, st>>>(vals, cols, offs, (const I*)p.blk_rows, (const I*)p.blk_win, sh.cap, sh.win_cap, xx, yy, dot);
         }

@@ -185,3 +185,15 @@ def test_full_size_headline_workload_properties(smb, ctx):
     x2 = x.clone()
     x2.scale(2.0)
     assert np.array_equal(a.mvp(x2).to_numpy(), 2.0 * ref)
+
+
+def test_small_matrix_sweep_all_variants_types_and_entry_points():
+    """scripts/sanitize_small.py: every kernel family x {f32,f64} x {u32,u64} on small ragged / power-law / banded / giant-row /
+    empty matrices, plus bilinear, CG, vector ops, to_crs and the chunked host path (regression: a banded plan whose dynamic +
+    static shared memory crossed 48 KB without the opt-in attribute failed to launch)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "scripts", "sanitize_small.py")], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0 and "sanitize_small: ok" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
