@@ -57,9 +57,14 @@ typedef enum {
                                 storage-order per-row sums (bit-exact for rows <= 64 nnz)            */
     SMB200_SPMV_STREAM_TMA = 4, /* K3 with values/columns brought in by cp.async.bulk (TMA)          */
     SMB200_SPMV_BANDED = 5,  /* K4: STREAM_TMA + the x window of the block staged in shared memory   */
-    SMB200_SPMV_STREAM_PIPE = 6 /* K3 persistent: one CTA per SM slot walks its row blocks through a
+    SMB200_SPMV_STREAM_PIPE = 6, /* K3 persistent: one CTA per SM slot walks its row blocks through a
                                 multi-stage shared-memory ring filled by cp.async.bulk (TMA) + mbarrier,
                                 so the HBM stream never waits for the gather / row-sum phases         */
+    SMB200_SPMV_RING = 7     /* K4 persistent, short rows (<= 32 entries: stencils, FEM): values, columns, row
+                                offsets, the block's x segments (up to 4 windows found at plan time) and
+                                the dot weights are ALL staged by TMA into a shared-memory ring; no
+                                synchronous global load is left in the loop.  Falls back to STREAM when
+                                the matrix has longer rows                                            */
 } smb200_spmv_variant;
 
 /* flags for smb200_crs_configure */
@@ -91,6 +96,7 @@ typedef struct {
     double mean_row_len;
     uint64_t algorithmic_bytes; /* nnz*(sizeof T + sizeof I) + (n_rows+1)*sizeof I + n_cols*sizeof T + n_rows*sizeof T */
     uint64_t launches_per_spmv;
+    uint64_t n_xwin_blocks;   /* RING: row blocks whose x segments are staged by TMA (the rest gather from global) */
 } smb200_plan_info;
 
 typedef struct {

@@ -64,7 +64,7 @@ def run(ctx, name, a, variants, reps=50, flush=False):
 def main():
     which = sys.argv[1:] or ["c2"]
     ctx = smb.Context(0)
-    V = [(smb.SPMV_STREAM, 0), (smb.SPMV_STREAM_TMA, 0), (smb.SPMV_STREAM_PIPE, 0), (smb.SPMV_VECTOR, 8), (smb.SPMV_VECTOR, 4),
+    V = [(smb.SPMV_STREAM, 0), (smb.SPMV_RING, 0), (smb.SPMV_STREAM_TMA, 0), (smb.SPMV_STREAM_PIPE, 0), (smb.SPMV_VECTOR, 8), (smb.SPMV_VECTOR, 4),
          (smb.SPMV_SCALAR, 0), (smb.SPMV_AUTO, 0)]
     for w in which:
         if w == "c1":

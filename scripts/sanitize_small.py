@@ -15,7 +15,7 @@ import sparsemat_b200 as smb  # noqa: E402
 
 ctx = smb.Context(0)
 V = [(smb.SPMV_SCALAR, 0), (smb.SPMV_VECTOR, 4), (smb.SPMV_VECTOR, 32), (smb.SPMV_STREAM, 0), (smb.SPMV_STREAM_TMA, 0),
-     (smb.SPMV_BANDED, 0), (smb.SPMV_STREAM_PIPE, 0)]
+     (smb.SPMV_BANDED, 0), (smb.SPMV_STREAM_PIPE, 0), (smb.SPMV_RING, 0)]
 for vdt, idt in ((np.float32, np.uint32), (np.float64, np.uint32), (np.float32, np.uint64), (np.float64, np.uint64)):
     mats = [cases.ragged(1, 700, 650, 30, vdt, idt), cases.powerlaw(2, 3000, 3000, 5000, vdt, idt), cases.banded(3, 5000, 200, 7, vdt, idt),
             cases.giant_row(4, 300, 20000, 30000, vdt, idt), cases.all_empty(9, 4, vdt, idt)]
@@ -36,7 +36,7 @@ for vdt, idt in ((np.float32, np.uint32), (np.float64, np.uint32), (np.float32, 
         lhs.fill_uniform(2)
         a.inner_prod(lhs, x)
     lap = smb.SparseMatCRS.laplace(ctx, vdt, idt, 12, 11, 10)
-    for v in (smb.SPMV_AUTO, smb.SPMV_STREAM, smb.SPMV_STREAM_PIPE, smb.SPMV_VECTOR):
+    for v in (smb.SPMV_AUTO, smb.SPMV_STREAM, smb.SPMV_STREAM_PIPE, smb.SPMV_RING, smb.SPMV_VECTOR):
         lap.configure(v)
         b = smb.DenseVec(ctx, 1320, vdt)
         b.fill(1.0)

@@ -17,9 +17,9 @@ LIB_PATH = os.path.join(_HERE, "lib", "libsmb200.so")
 OK, ERR_INVALID, ERR_DIM, ERR_CUDA, ERR_NOT_SQUARE, ERR_SIZE_MISMATCH, ERR_NCCL, ERR_UNSUPPORTED, ERR_OOM = range(9)
 F32, F64 = 0, 1
 U32, U64 = 0, 1
-SPMV_AUTO, SPMV_SCALAR, SPMV_VECTOR, SPMV_STREAM, SPMV_STREAM_TMA, SPMV_BANDED, SPMV_STREAM_PIPE = range(7)
+SPMV_AUTO, SPMV_SCALAR, SPMV_VECTOR, SPMV_STREAM, SPMV_STREAM_TMA, SPMV_BANDED, SPMV_STREAM_PIPE, SPMV_RING = range(8)
 FLAG_L2_PERSIST_X = 1
-VARIANT_NAMES = {0: "auto", 1: "scalar", 2: "vector", 3: "stream", 4: "stream_tma", 5: "banded", 6: "stream_pipe"}
+VARIANT_NAMES = {0: "auto", 1: "scalar", 2: "vector", 3: "stream", 4: "stream_tma", 5: "banded", 6: "stream_pipe", 7: "ring"}
 
 
 class Panic(RuntimeError):
@@ -41,7 +41,8 @@ class DevInfo(C.Structure):
 class PlanInfo(C.Structure):
     _fields_ = [("variant", C.c_int32), ("lanes", C.c_int32), ("flags", C.c_uint32), ("n_blocks", C.c_uint64),
                 ("n_rows", C.c_uint64), ("n_cols", C.c_uint64), ("nnz", C.c_uint64), ("max_row_len", C.c_uint64),
-                ("mean_row_len", C.c_double), ("algorithmic_bytes", C.c_uint64), ("launches_per_spmv", C.c_uint64)]
+                ("mean_row_len", C.c_double), ("algorithmic_bytes", C.c_uint64), ("launches_per_spmv", C.c_uint64),
+                ("n_xwin_blocks", C.c_uint64)]
 
 
 class CgStats(C.Structure):

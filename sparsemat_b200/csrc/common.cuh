@@ -114,6 +114,10 @@ struct SpmvPlan {
     void* blk_rows = nullptr;           // STREAM*: [n_blocks+1] row split points, index type
     void* blk_nnz = nullptr;            // STREAM*: [n_blocks+1] offset_rows[blk_rows[k]], index type
     unsigned char* blk_flags = nullptr; // PIPE: per block, kBlkNoFit | kBlkLong
+    unsigned long long* seg_lo = nullptr; // RING: [4 * n_blocks] first column of each x segment of the block (aligned down)
+    unsigned* seg_len = nullptr;        // RING: [4 * n_blocks] segment lengths in elements (0 = unused; all 0 = no window)
+    unsigned ocap = 0, xcap = 0;        // RING: row-offset / x-window capacity of a stage (elements)
+    uint64_t n_xwin = 0;                // RING: blocks whose columns fit <= 4 windows
     unsigned cap = 0, target = 0;       // STREAM*: staging capacity / merge target the plan was cut for (elements)
     void* blk_win = nullptr;            // BANDED: [2*n_blocks] (cmin, cmax+1) per block, index type
     uint64_t max_win = 0;               // BANDED: widest window (elements)

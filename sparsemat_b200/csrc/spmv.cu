@@ -685,11 +685,249 @@ spmv_pipe_kernel(const T* __restrict__ vals, const I* __restrict__ cols, const I
     if constexpr (DOT) finish_dot<T, THREADS>(acc, dot);
 }
 
+// ---- K4 persistent ring: everything staged by TMA -------------------------------------------------------------
+// For matrices whose rows are short (<= kRowMajorMax entries: stencils, FEM).  One 512-thread CTA per SM walks the
+// row blocks b = blockIdx.x, blockIdx.x + gridDim.x, ...  Thread 0 keeps `stages` blocks staged or in flight; one
+// stage holds the block's slice of values and columns, its row offsets, up to kNSeg windows of x that cover every
+// column the block touches (found once at plan time).  All of it arrives by cp.async.bulk on the stage's mbarrier, so
+// the only synchronous memory operations left in the loop are shared-memory loads, the coalesced store of y and, for
+// the fused dot, one coalesced load of the row's weight.  A producer warp (lane 0) fills the ring; the other 15 warps
+// consume it without any block-wide barrier: a warp releases a stage (mbarrier `empty`) as soon as its own rows are done.  One thread per row sums in storage order (bit-exact vs the
+// reference); lanes hold consecutive rows, so slice reads have an odd word stride and window reads are consecutive.
+constexpr int kNSeg = 4;
+constexpr int kSegWords = 4096;              // plan time: bitmap over 131072 column buckets
+constexpr int kRingThreads = 512;
+
+struct RingDesc {
+    unsigned long long r0, r1, a0, r0a;
+    unsigned long long lo[kNSeg];            // first column of each window (unused: all ones)
+    long long delta[kNSeg];                  // window element index = column + delta
+    unsigned xwin;                           // 1: the windows cover the block; 0: gather x from global memory
+};
+
+template <class T, class I, int NSEG> struct RingWin {
+    I lo1, lo2, lo3;
+    unsigned d0, d1, d2, d3;          // window element index = (unsigned)column + d  (mod 2^32: windows are < 2^32 long)
+    __device__ __forceinline__ unsigned at(I c) const {
+        unsigned d = d0;
+        if constexpr (NSEG > 1) { if (c >= lo1) d = d1; }
+        if constexpr (NSEG > 2) { if (c >= lo2) d = d2; }
+        if constexpr (NSEG > 3) { if (c >= lo3) d = d3; }
+        return (unsigned)c + d;
+    }
+};
+
+// Rows [r0, r1) of one staged block, one thread per row, starting at thread `lane_id` of `n_lanes` consumer threads.
+template <class T, class I, bool DOT, int NSEG>
+__device__ __forceinline__ double ring_rows(const T* sv, const I* sc, const I* so, const T* sx, const RingDesc& d,
+                                            unsigned lane_id, unsigned n_lanes, const T* __restrict__ x, T* __restrict__ y,
+                                            const T* __restrict__ w) {
+    const uint64_t r0 = d.r0, r1 = d.r1, a0 = d.a0, r0a = d.r0a;
+    RingWin<T, I, NSEG> win;
+    win.lo1 = (I)d.lo[1]; win.lo2 = (I)d.lo[2]; win.lo3 = (I)d.lo[3];
+    win.d0 = (unsigned)d.delta[0]; win.d1 = (unsigned)d.delta[1]; win.d2 = (unsigned)d.delta[2]; win.d3 = (unsigned)d.delta[3];
+    double acc = 0.0;
+    for (uint64_t r = r0 + lane_id; r < r1; r += n_lanes) {
+        const unsigned ka = (unsigned)((uint64_t)so[r - r0a] - a0), ke = (unsigned)((uint64_t)so[r + 1 - r0a] - a0);
+        T wv = T(0);
+        if constexpr (DOT) wv = __ldg(w + r);          // one coalesced load per row, in flight during the row's sum
+        T sum = T(0);
+#pragma unroll 4
+        for (unsigned k = ka; k < ke; ++k) {
+            const I c = sc[k];
+            T xv;
+            if constexpr (NSEG > 0) xv = sx[win.at(c)];
+            else xv = __ldg(x + (size_t)c);
+            sum = add_rn(sum, mul_rn(xv, sv[k]));
+        }
+        y[r] = sum;
+        if constexpr (DOT) acc += (double)mul_rn(wv, sum);
+    }
+    return acc;
+}
+
+template <class T, class I, bool DOT>
+__global__ void __launch_bounds__(kRingThreads, 2)
+spmv_ring_kernel(const T* __restrict__ vals, const I* __restrict__ cols, const I* __restrict__ offs,
+                 const I* __restrict__ blk_rows, const I* __restrict__ blk_nnz, const unsigned long long* __restrict__ seg_lo,
+                 const unsigned* __restrict__ seg_len, unsigned n_blocks, unsigned cap, unsigned ocap, unsigned xcap,
+                 unsigned stages, int xwin_ok, const T* __restrict__ x, T* __restrict__ y, DotArgs dot) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t full[kPipeMaxStages];    // producer -> consumers: the stage's bytes have landed
+    __shared__ __align__(8) uint64_t empty[kPipeMaxStages];   // consumers -> producer: every consumer warp has left the stage
+    __shared__ RingDesc s_desc[kPipeMaxStages];
+    constexpr unsigned OA = 16 / sizeof(I);
+    constexpr unsigned kConsumerWarps = kRingThreads / 32 - 1;
+    const unsigned tid = threadIdx.x;
+    const size_t o_cols = (size_t)cap * sizeof(T);
+    const size_t o_offs = o_cols + (size_t)cap * sizeof(I);
+    const size_t o_x = o_offs + (size_t)(ocap + 8) * sizeof(I);
+    const size_t stage_bytes = o_x + (size_t)xcap * sizeof(T);
+    double stop = 0.0;
+    if constexpr (DOT) { if (dot.done != nullptr) stop = __ldcg(dot.done); }
+    if (stop != 0.0) return;
+    const unsigned n_my = blockIdx.x < n_blocks ? (n_blocks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    if (tid == 0)
+        for (unsigned s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kConsumerWarps); }
+    __syncthreads();
+    double acc = 0.0;
+
+    if (tid < 32) {
+        // ---- producer warp: lane 0 runs ahead of the consumers, bounded only by the ring depth --------------------------
+        if (tid == 0) {
+            unsigned s = 0, parity = 0;
+            for (unsigned j = 0; j < n_my; ++j) {
+                const size_t b = (size_t)blockIdx.x + (size_t)j * gridDim.x;
+                const unsigned long long r0 = (unsigned long long)__ldg(blk_rows + b), r1 = (unsigned long long)__ldg(blk_rows + b + 1);
+                const unsigned long long n0 = (unsigned long long)__ldg(blk_nnz + b), n1 = (unsigned long long)__ldg(blk_nnz + b + 1);
+                unsigned long long lo[kNSeg];
+                unsigned len[kNSeg];
+#pragma unroll
+                for (int i = 0; i < kNSeg; ++i) { lo[i] = __ldg(seg_lo + kNSeg * b + i); len[i] = __ldg(seg_len + kNSeg * b + i); }
+                if (j >= stages) mbar_wait(&empty[s], parity ^ 1u);     // the consumers have drained this stage's previous block
+                RingDesc& d = s_desc[s];
+                unsigned char* base = smem_raw + (size_t)s * stage_bytes;
+                const unsigned long long a0 = n0 & ~3ull, r0a = r0 & ~(unsigned long long)(OA - 1);
+                const unsigned count = (unsigned)(((n1 - a0) + 3ull) & ~3ull);
+                const unsigned ocount = (unsigned)(((r1 + 1 - r0a) + (OA - 1)) & ~(unsigned long long)(OA - 1));
+                d.r0 = r0; d.r1 = r1; d.a0 = a0; d.r0a = r0a;
+                unsigned xtotal = 0, nseg = 0;
+#pragma unroll
+                for (int i = 0; i < kNSeg; ++i) {
+                    d.lo[i] = len[i] ? lo[i] : ~0ull;
+                    d.delta[i] = (long long)xtotal - (long long)lo[i];
+                    xtotal += len[i];
+                    nseg += len[i] ? 1u : 0u;
+                }
+                const bool xw = xwin_ok && xtotal > 0;
+                d.xwin = xw ? nseg : 0u;
+                unsigned bytes = count * (unsigned)(sizeof(T) + sizeof(I)) + ocount * (unsigned)sizeof(I);
+                if (xw) bytes += xtotal * (unsigned)sizeof(T);
+                mbar_expect_tx(&full[s], bytes);
+                if (count) {
+                    bulk_g2s(base, vals + a0, count * (unsigned)sizeof(T), &full[s]);
+                    bulk_g2s(base + o_cols, cols + a0, count * (unsigned)sizeof(I), &full[s]);
+                }
+                bulk_g2s(base + o_offs, offs + r0a, ocount * (unsigned)sizeof(I), &full[s]);
+                if (xw) {
+                    unsigned at = 0;
+#pragma unroll
+                    for (int i = 0; i < kNSeg; ++i)
+                        if (len[i]) { bulk_g2s(base + o_x + (size_t)at * sizeof(T), x + lo[i], len[i] * (unsigned)sizeof(T), &full[s]); at += len[i]; }
+                }
+                if (++s == stages) { s = 0; parity ^= 1u; }
+            }
+        }
+    } else {
+        // ---- consumer warps: no block-wide barrier; a warp releases the stage as soon as its own rows are done ------------
+        const unsigned lane_id = tid - 32, n_lanes = kRingThreads - 32;
+        unsigned s = 0, parity = 0;
+        for (unsigned i = 0; i < n_my; ++i) {
+            mbar_wait(&full[s], parity);
+            const RingDesc d = s_desc[s];
+            const unsigned char* base = smem_raw + (size_t)s * stage_bytes;
+            const T* sv = reinterpret_cast<const T*>(base);
+            const I* sc = reinterpret_cast<const I*>(base + o_cols);
+            const I* so = reinterpret_cast<const I*>(base + o_offs);
+            const T* sx = reinterpret_cast<const T*>(base + o_x);
+            const T* w = (const T*)dot.w;
+            switch (d.xwin) {                     // number of x windows of the block (block-uniform)
+                case 0: acc += ring_rows<T, I, DOT, 0>(sv, sc, so, sx, d, lane_id, n_lanes, x, y, w); break;
+                case 1: acc += ring_rows<T, I, DOT, 1>(sv, sc, so, sx, d, lane_id, n_lanes, x, y, w); break;
+                case 2: acc += ring_rows<T, I, DOT, 2>(sv, sc, so, sx, d, lane_id, n_lanes, x, y, w); break;
+                case 3: acc += ring_rows<T, I, DOT, 3>(sv, sc, so, sx, d, lane_id, n_lanes, x, y, w); break;
+                default: acc += ring_rows<T, I, DOT, 4>(sv, sc, so, sx, d, lane_id, n_lanes, x, y, w); break;
+            }
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(&empty[s]);
+            if (++s == stages) { s = 0; parity ^= 1u; }
+        }
+    }
+    if constexpr (DOT) finish_dot<T, kRingThreads>(acc, dot);
+}
+
+// Plan time, one CTA per block: find <= kNSeg windows of x that cover every column of the block.  Columns are
+// bucketed (2^shift columns per bucket) into a shared-memory bitmap, runs of set buckets (gaps of one bucket are
+// bridged) become windows, a second pass takes the exact [min, max] of each; blocks whose windows do not fit
+// `xcap` elements, or that need more than kNSeg, get no window and gather from global memory.
+template <class I>
+__global__ void __launch_bounds__(128)
+block_segments_kernel(const I* __restrict__ cols, const I* __restrict__ blk_nnz, unsigned shift, unsigned xcap, unsigned xalign,
+                      unsigned long long* __restrict__ seg_lo, unsigned* __restrict__ seg_len, unsigned long long* __restrict__ n_ok) {
+    __shared__ unsigned bitmap[kSegWords];
+    __shared__ unsigned long long s_lo[kNSeg], s_hi[kNSeg];
+    __shared__ unsigned run_b0[kNSeg], run_b1[kNSeg];
+    __shared__ int s_nruns;
+    __shared__ unsigned s_bmin, s_bmax;
+    const size_t b = blockIdx.x;
+    const uint64_t n0 = (uint64_t)blk_nnz[b], n1 = (uint64_t)blk_nnz[b + 1];
+    for (unsigned i = threadIdx.x; i < (unsigned)kSegWords; i += 128) bitmap[i] = 0u;
+    if (threadIdx.x == 0) { s_bmin = 0xffffffffu; s_bmax = 0u; s_nruns = 0; }
+    if (threadIdx.x < kNSeg) { s_lo[threadIdx.x] = ~0ull; s_hi[threadIdx.x] = 0ull; }
+    __syncthreads();
+    unsigned bmin = 0xffffffffu, bmax = 0u;
+    for (uint64_t k = n0 + threadIdx.x; k < n1; k += 128) {
+        const unsigned bk = (unsigned)((uint64_t)cols[k] >> shift);
+        atomicOr(&bitmap[bk >> 5], 1u << (bk & 31));
+        bmin = bk < bmin ? bk : bmin;
+        bmax = bk > bmax ? bk : bmax;
+    }
+    if (n1 > n0) { atomicMin(&s_bmin, bmin); atomicMax(&s_bmax, bmax); }
+    __syncthreads();
+    if (threadIdx.x == 0 && n1 > n0) {
+        int nr = 0;
+        unsigned last = 0;
+        for (unsigned wd = s_bmin >> 5; wd <= (s_bmax >> 5) && nr <= kNSeg; ++wd) {
+            unsigned bits = bitmap[wd];
+            while (bits) {
+                const unsigned bk = wd * 32u + (unsigned)(__ffs((int)bits) - 1);
+                bits &= bits - 1u;
+                if (nr > 0 && bk <= last + 2u) run_b1[nr - 1] = bk;            // same run (a one-bucket gap is bridged)
+                else if (nr == kNSeg) { nr = kNSeg + 1; break; }
+                else { run_b0[nr] = bk; run_b1[nr] = bk; ++nr; }
+                last = bk;
+            }
+        }
+        s_nruns = nr;
+    }
+    __syncthreads();
+    const int nr = s_nruns;
+    if (nr >= 1 && nr <= kNSeg) {
+        for (uint64_t k = n0 + threadIdx.x; k < n1; k += 128) {
+            const unsigned long long c = (unsigned long long)cols[k];
+            const unsigned bk = (unsigned)(c >> shift);
+            int i = 0;
+            while (i + 1 < nr && bk > run_b1[i]) ++i;
+            atomicMin(&s_lo[i], c);
+            atomicMax(&s_hi[i], c + 1ull);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long lo[kNSeg];
+        unsigned len[kNSeg], total = 0;
+        bool ok = nr >= 1 && nr <= kNSeg;
+        for (int i = 0; i < kNSeg; ++i) { lo[i] = ~0ull; len[i] = 0; }
+        if (ok) {
+            for (int i = 0; i < nr; ++i) {
+                lo[i] = s_lo[i] & ~(unsigned long long)(xalign - 1);
+                const unsigned long long l = (s_hi[i] - lo[i] + (xalign - 1)) & ~(unsigned long long)(xalign - 1);
+                if (l > (unsigned long long)xcap) { ok = false; break; }
+                len[i] = (unsigned)l;
+                total += len[i];
+            }
+            if (total > xcap) ok = false;
+        }
+        for (int i = 0; i < kNSeg; ++i) { seg_lo[kNSeg * b + i] = ok ? lo[i] : ~0ull; seg_len[kNSeg * b + i] = ok ? len[i] : 0u; }
+        if (ok) atomicAdd(n_ok, 1ull);
+    }
+}
+
 // ---- plan construction --------------------------------------------------------------------------------
 // Split points of the merge coordinate key(r) = (r - rb) + (offs[r] - offs[rb]) at multiples of `target`.
 template <class I>
-__global__ void split_rows_kernel(const I* __restrict__ offs, uint64_t rb, uint64_t re, uint64_t target, uint64_t n_blocks,
-                                  I* __restrict__ blk_rows, I* __restrict__ blk_nnz) {
+__global__ void split_rows_kernel(const I* __restrict__ offs, uint64_t rb, uint64_t re, uint64_t target, uint64_t row_weight,
+                                  uint64_t n_blocks, I* __restrict__ blk_rows, I* __restrict__ blk_nnz) {
     const uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (k > n_blocks) return;
     if (k == n_blocks) { blk_rows[k] = (I)re; blk_nnz[k] = offs[re]; return; }
@@ -698,7 +936,7 @@ __global__ void split_rows_kernel(const I* __restrict__ offs, uint64_t rb, uint6
     uint64_t lo = rb, hi = re;          // smallest r in [rb,re] with key(r) >= want
     while (lo < hi) {
         const uint64_t mid = lo + ((hi - lo) >> 1);
-        const uint64_t key = (mid - rb) + ((uint64_t)offs[mid] - base);
+        const uint64_t key = (mid - rb) * row_weight + ((uint64_t)offs[mid] - base);
         if (key < want) lo = mid + 1; else hi = mid;
     }
     blk_rows[k] = (I)lo;
@@ -788,6 +1026,8 @@ void plan_free(SpmvPlan& p) {
     if (p.blk_rows) cudaFree(p.blk_rows);
     if (p.blk_nnz) cudaFree(p.blk_nnz);
     if (p.blk_flags) cudaFree(p.blk_flags);
+    if (p.seg_lo) cudaFree(p.seg_lo);
+    if (p.seg_len) cudaFree(p.seg_len);
     if (p.blk_win) cudaFree(p.blk_win);
     p = SpmvPlan();
 }
@@ -812,6 +1052,11 @@ static void stream_shape(const smb200_crs* m, int variant, unsigned* cap, unsign
     unsigned c, t;
     if (variant == SMB200_SPMV_STREAM) {
         c = m->vt == SMB200_F64 ? 3584u : 4608u;
+    } else if (variant == SMB200_SPMV_RING) {
+        // 36 KB of values + columns per stage (measured best on the 7-point Laplacian: f32/u32 4608, f64/u32 3072)
+        const size_t per = vsize(m->vt) + isize(m->it);
+        c = (unsigned)((36u * 1024u) / per) & ~3u;
+        c = (unsigned)env_int("SMB200_RING_CAP", (int)c) & ~3u;
     } else if (variant == SMB200_SPMV_STREAM_PIPE) {
         // one ring stage: 32 KB of values + columns
         const size_t per = vsize(m->vt) + isize(m->it);
@@ -826,6 +1071,7 @@ static void stream_shape(const smb200_crs* m, int variant, unsigned* cap, unsign
     if (c < 256) c = 256;
     if (c > kMaxCap) c = kMaxCap;
     t = c - c / 9;                     // leave room for the row that straddles the target
+    if (variant == SMB200_SPMV_RING) t = c - (unsigned)kRowMajorMax - 8;   // rows are short: a block overshoots by < one row
     t = (unsigned)env_int("SMB200_STREAM_TARGET", (int)t);
     if (t + 8 > c) t = c - 8;
     *cap = c;
@@ -844,8 +1090,25 @@ static PlanShape g_shape_of_plan(const smb200_crs* m, const SpmvPlan& p) {
     return s;
 }
 
+static smb200_status plan_build_range_impl(smb200_crs* m, SpmvPlan& p, int want_variant, int want_lanes, uint32_t flags,
+                                           uint64_t rb, uint64_t re);
+
+// AUTO: short-row matrices that do not live in L2 try the TMA ring first; it is kept when (almost) every block got its
+// x windows (stencils, banded, FEM-like), otherwise the stream kernel — which gathers x through L1/L2 — is planned.
 smb200_status plan_build_range(smb200_crs* m, SpmvPlan& p, int want_variant, int want_lanes, uint32_t flags,
                                uint64_t rb, uint64_t re) {
+    int want = want_variant;
+    if (want == SMB200_SPMV_AUTO) want = env_int("SMB200_SPMV_VARIANT", SMB200_SPMV_AUTO);
+    const uint64_t bytes = m->nnz * (vsize(m->vt) + isize(m->it)) + (m->n_rows + 1) * isize(m->it) + (m->n_cols + m->n_rows) * vsize(m->vt);
+    if (want == SMB200_SPMV_AUTO && m->max_row_len <= (uint64_t)kRowMajorMax && m->nnz > 0 && bytes * 3 >= (uint64_t)m->ctx->l2_bytes * 2) {
+        SMB_TRY(plan_build_range_impl(m, p, SMB200_SPMV_RING, want_lanes, flags, rb, re));
+        if (p.variant == SMB200_SPMV_RING && p.n_xwin * 10 >= p.n_blocks * 8) return SMB200_OK;
+    }
+    return plan_build_range_impl(m, p, want_variant, want_lanes, flags, rb, re);
+}
+
+static smb200_status plan_build_range_impl(smb200_crs* m, SpmvPlan& p, int want_variant, int want_lanes, uint32_t flags,
+                                           uint64_t rb, uint64_t re) {
     smb200_ctx* ctx = m->ctx;
     plan_free(p);
     p.flags = flags;
@@ -862,6 +1125,8 @@ smb200_status plan_build_range(smb200_crs* m, SpmvPlan& p, int want_variant, int
         const uint64_t bytes = m->nnz * (vsize(m->vt) + isize(m->it)) + (m->n_rows + 1) * isize(m->it) + (m->n_cols + m->n_rows) * vsize(m->vt);
         if (bytes * 3 < (uint64_t)ctx->l2_bytes * 2 && m->max_row_len <= 16) variant = SMB200_SPMV_SCALAR;
     }
+    // RING needs short rows everywhere (its stages have no long-row path)
+    if (variant == SMB200_SPMV_RING && m->max_row_len > (uint64_t)kRowMajorMax) variant = SMB200_SPMV_STREAM;
     p.variant = variant;
     p.lanes = 0;
     if (variant == SMB200_SPMV_SCALAR) p.lanes = 1;
@@ -891,17 +1156,51 @@ smb200_status plan_build_range(smb200_crs* m, SpmvPlan& p, int want_variant, int
             SMB_CUDA(cudaStreamSynchronize(ctx->stream));
             ob = b32; oe = e32;
         }
-        const uint64_t merge_len = rows + (oe - ob);
+        // RING bounds the rows of a block as well (their offsets are staged): key = 2*rows + nnz
+        const uint64_t row_weight = variant == SMB200_SPMV_RING ? 2 : 1;
+        if (variant == SMB200_SPMV_RING) {
+            // two CTAs/SM x two stages: (values + columns) + offsets + x windows of one stage <= ~56 KB
+            p.ocap = (target / 2 + 8) & ~3u;
+            const size_t budget = 55 * 1024, fixed = (size_t)cap * (vsize(m->vt) + isize(m->it)) + (size_t)(p.ocap + 8) * isize(m->it);
+            unsigned xc = budget > fixed ? (unsigned)((budget - fixed) / vsize(m->vt)) : 0u;
+            if (xc > cap) xc = cap;
+            p.xcap = (unsigned)env_int("SMB200_RING_XCAP", (int)xc) & ~3u;
+        }
+        const uint64_t merge_len = rows * row_weight + (oe - ob);
         p.n_blocks = (merge_len + target - 1) / target;
         if (p.n_blocks == 0) p.n_blocks = 1;
         SMB_REQUIRE(p.n_blocks < 0x7FFFFFFFull, SMB200_ERR_UNSUPPORTED, "spmv: too many row blocks");
         SMB_CUDA(cudaMalloc(&p.blk_rows, (p.n_blocks + 1) * is));
         SMB_CUDA(cudaMalloc(&p.blk_nnz, (p.n_blocks + 1) * is));
         const unsigned g = (unsigned)((p.n_blocks + 1 + 255) / 256);
-        if (m->it == SMB200_U64) split_rows_kernel<uint64_t><<<g, 256, 0, ctx->stream>>>((const uint64_t*)m->offsets, rb, re, target, p.n_blocks, (uint64_t*)p.blk_rows, (uint64_t*)p.blk_nnz);
-        else split_rows_kernel<uint32_t><<<g, 256, 0, ctx->stream>>>((const uint32_t*)m->offsets, rb, re, target, p.n_blocks, (uint32_t*)p.blk_rows, (uint32_t*)p.blk_nnz);
+        if (m->it == SMB200_U64) split_rows_kernel<uint64_t><<<g, 256, 0, ctx->stream>>>((const uint64_t*)m->offsets, rb, re, target, row_weight, p.n_blocks, (uint64_t*)p.blk_rows, (uint64_t*)p.blk_nnz);
+        else split_rows_kernel<uint32_t><<<g, 256, 0, ctx->stream>>>((const uint32_t*)m->offsets, rb, re, target, row_weight, p.n_blocks, (uint32_t*)p.blk_rows, (uint32_t*)p.blk_nnz);
         count_launch();
         SMB_CUDA(cudaGetLastError());
+        if (variant == SMB200_SPMV_RING) {
+            SMB_CUDA(cudaMalloc(&p.seg_lo, (size_t)kNSeg * p.n_blocks * sizeof(unsigned long long)));
+            SMB_CUDA(cudaMalloc(&p.seg_len, (size_t)kNSeg * p.n_blocks * sizeof(unsigned)));
+            unsigned long long* d_ok = nullptr;
+            SMB_CUDA(cudaMalloc(&d_ok, sizeof(unsigned long long)));
+            cudaMemsetAsync(d_ok, 0, sizeof(unsigned long long), ctx->stream);
+            unsigned shift = 6;                                     // >= 64 columns per bucket, <= 131072 buckets
+            while (((m->n_cols + ((1ull << shift) - 1)) >> shift) > (uint64_t)kSegWords * 32u) ++shift;
+            const unsigned xalign = (unsigned)(16 / vsize(m->vt));
+            if (m->nnz) {
+                if (m->it == SMB200_U64) block_segments_kernel<uint64_t><<<(unsigned)p.n_blocks, 128, 0, ctx->stream>>>((const uint64_t*)m->columns, (const uint64_t*)p.blk_nnz, shift, p.xcap, xalign, p.seg_lo, p.seg_len, d_ok);
+                else block_segments_kernel<uint32_t><<<(unsigned)p.n_blocks, 128, 0, ctx->stream>>>((const uint32_t*)m->columns, (const uint32_t*)p.blk_nnz, shift, p.xcap, xalign, p.seg_lo, p.seg_len, d_ok);
+                count_launch();
+            } else {
+                cudaMemsetAsync(p.seg_len, 0, (size_t)kNSeg * p.n_blocks * sizeof(unsigned), ctx->stream);
+                cudaMemsetAsync(p.seg_lo, 0xff, (size_t)kNSeg * p.n_blocks * sizeof(unsigned long long), ctx->stream);
+            }
+            unsigned long long h_ok = 0;
+            cudaError_t e = cudaMemcpyAsync(&h_ok, d_ok, sizeof h_ok, cudaMemcpyDeviceToHost, ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+            cudaFree(d_ok);
+            SMB_CUDA(e);
+            p.n_xwin = h_ok;
+        }
         if (variant == SMB200_SPMV_STREAM_PIPE) {
             SMB_CUDA(cudaMalloc(&p.blk_flags, p.n_blocks));
             const unsigned gf = (unsigned)((p.n_blocks + 127) / 128);
@@ -943,6 +1242,7 @@ smb200_status plan_build(smb200_crs* m) {
 }
 
 // ---- launch ---------------------------------------------------------------------------------------------
+static thread_local bool g_x_unpadded = false;        // smb200_spmv: x / w are caller-owned device memory without tail padding
 static thread_local unsigned g_last_pipe_grid = 0;   // CTAs of the most recent persistent launch (= its dot partials)
 
 template <class T, class I, bool DOT>
@@ -975,6 +1275,33 @@ static smb200_status launch_typed(smb200_crs* m, const SpmvPlan& p, uint64_t rb,
             if (smem > 32 * 1024) SMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             if (carve >= 0) SMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
             kern<<<(unsigned)p.n_blocks, kSpmvThreads, smem, st>>>(vals, cols, offs, (const I*)p.blk_rows, (const I*)p.blk_nnz, sh.cap, xx, yy, dot);
+        } else if (p.variant == SMB200_SPMV_RING) {
+            const size_t stage = (size_t)sh.cap * (sizeof(T) + sizeof(I)) + (size_t)(p.ocap + 8) * sizeof(I) + (size_t)p.xcap * sizeof(T);
+            // two CTAs per SM, two stages each: one block is consumed while the next one lands, and the second CTA's
+            // consumers fill the issue slots the first one leaves idle
+            int ctas = env_int("SMB200_RING_CTAS", 2);
+            if (ctas < 1) ctas = 1;
+            if (ctas > 2) ctas = 2;
+            int stages = env_int("SMB200_RING_STAGES", ctas == 2 ? 2 : 4);
+            if (stages < 2) stages = 2;
+            if (stages > kPipeMaxStages) stages = kPipeMaxStages;
+            while (stages > 2 && (stage * stages + 3072) * ctas > 227u * 1024u) --stages;
+            if ((stage * stages + 3072) * ctas > 227u * 1024u) ctas = 1;
+            const size_t smem = stage * stages;
+            SMB_REQUIRE(smem <= 224u * 1024u, SMB200_ERR_INVALID, "spmv: ring stage of %zu bytes does not fit shared memory", stage);
+            auto kern = spmv_ring_kernel<T, I, DOT>;
+            SMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int resident = 0;
+            SMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, kRingThreads, smem));
+            if (resident < 1) resident = 1;
+            if (resident > ctas) resident = ctas;
+            uint64_t grid = (uint64_t)ctx->sm_count * (uint64_t)resident;
+            if (grid > p.n_blocks) grid = p.n_blocks;
+            g_last_pipe_grid = (unsigned)grid;
+            // bulk copies need 16-byte aligned sources whose rounded-up tails stay inside the allocation
+            const int xwin_ok = (((uintptr_t)x & 15u) == 0 && !g_x_unpadded && env_int("SMB200_RING_XWIN", 1) != 0) ? 1 : 0;
+            kern<<<(unsigned)grid, kRingThreads, smem, st>>>(vals, cols, offs, (const I*)p.blk_rows, (const I*)p.blk_nnz, p.seg_lo, p.seg_len,
+                                                           (unsigned)p.n_blocks, sh.cap, p.ocap, p.xcap, (unsigned)stages, xwin_ok, xx, yy, dot);
         } else if (p.variant == SMB200_SPMV_STREAM_PIPE) {
             int stages = env_int("SMB200_PIPE_STAGES", 3);
             if (stages < 3) stages = 3;     // the kernel reads the descriptor of block i + 1 during iteration i
@@ -1023,7 +1350,7 @@ static smb200_status launch_typed(smb200_crs* m, const SpmvPlan& p, uint64_t rb,
     if constexpr (DOT) {
         unsigned n_partials;
         if (p.variant == SMB200_SPMV_SCALAR || p.variant == SMB200_SPMV_VECTOR) n_partials = (unsigned)(((re - rb) + (kSpmvThreads / p.lanes) - 1) / (kSpmvThreads / p.lanes));
-        else if (p.variant == SMB200_SPMV_STREAM_PIPE) n_partials = g_last_pipe_grid;
+        else if (p.variant == SMB200_SPMV_STREAM_PIPE || p.variant == SMB200_SPMV_RING) n_partials = g_last_pipe_grid;
         else n_partials = (unsigned)p.n_blocks;
         spmv_dot_finalize_kernel<<<1, kFinalizeThreads, 0, st>>>(dot.partials, n_partials, sizeof(T) == 4 ? 1 : 0, dot.result,
                                                                dot.roll_dst, dot.roll_src, dot.done);
@@ -1118,7 +1445,7 @@ extern "C" {
 
 smb200_status smb200_crs_configure(smb200_crs* m, smb200_spmv_variant variant, int32_t lanes, uint32_t flags) {
     SMB_REQUIRE(m, SMB200_ERR_INVALID, "crs_configure: NULL argument");
-    SMB_REQUIRE(variant >= SMB200_SPMV_AUTO && variant <= SMB200_SPMV_STREAM_PIPE, SMB200_ERR_INVALID, "crs_configure: bad variant %d", (int)variant);
+    SMB_REQUIRE(variant >= SMB200_SPMV_AUTO && variant <= SMB200_SPMV_RING, SMB200_ERR_INVALID, "crs_configure: bad variant %d", (int)variant);
     m->want_variant = variant;
     m->want_lanes = lanes;
     m->want_flags = flags;
@@ -1146,6 +1473,7 @@ smb200_status smb200_crs_plan_info(const smb200_crs* cm, smb200_plan_info* out) 
     out->algorithmic_bytes = m->nnz * (vsize(m->vt) + isize(m->it)) + (m->n_rows + 1) * isize(m->it) +
                              m->n_cols * vsize(m->vt) + m->n_rows * vsize(m->vt);
     out->launches_per_spmv = 1;
+    out->n_xwin_blocks = m->plan.n_xwin;
     return SMB200_OK;
 }
 
@@ -1160,7 +1488,10 @@ smb200_status smb200_spmv(smb200_crs* a, const smb200_vec* x, smb200_vec* y) {
                 (unsigned long long)(a->n_cols - a->x_extra));
     SMB_REQUIRE(y->n >= a->n_rows, SMB200_ERR_DIM, "Dimension mismatch: y has %llu entries, matrix has %llu rows",
                 (unsigned long long)y->n, (unsigned long long)a->n_rows);
-    return spmv_launch(a, x->d, y->d, nullptr, 0);
+    g_x_unpadded = !x->owned;             // borrowed memory (smb200_vec_wrap) has no padding behind its last element
+    const smb200_status st = spmv_launch(a, x->d, y->d, nullptr, 0);
+    g_x_unpadded = false;
+    return st;
 }
 
 smb200_status smb200_spmv_host(smb200_crs* a, const void* x_host, uint64_t nx, void* y_host) {

@@ -97,7 +97,7 @@ def test_cg_matches_the_oracle_solver(smb, orc, ctx, vdt, tol, n):
     N = n ** 3
     xstar = orc.uniform(vdt, 6, N)
     b = orc.mvp(vals, cols, offs, xstar)
-    for variant in (smb.SPMV_AUTO, smb.SPMV_VECTOR, smb.SPMV_STREAM_TMA, smb.SPMV_STREAM_PIPE):
+    for variant in (smb.SPMV_AUTO, smb.SPMV_VECTOR, smb.SPMV_STREAM_TMA, smb.SPMV_STREAM_PIPE, smb.SPMV_RING):
         a.configure(variant)
         x = smb.DenseVec(ctx, N, vdt)
         st = smb.ConjugateGradient(tol, 2000, relative=True).solve_with_stats(a, smb.DenseVec.from_vec(ctx, b), x)

@@ -17,7 +17,7 @@ COMBOS = [(F32, U32), (F64, U32), (F32, U64), (F64, U64)]
 
 def _variants(smb):
     return [(smb.SPMV_SCALAR, 0), (smb.SPMV_VECTOR, 2), (smb.SPMV_VECTOR, 4), (smb.SPMV_VECTOR, 8), (smb.SPMV_VECTOR, 16),
-            (smb.SPMV_VECTOR, 32), (smb.SPMV_STREAM, 0), (smb.SPMV_STREAM_TMA, 0), (smb.SPMV_BANDED, 0), (smb.SPMV_STREAM_PIPE, 0), (smb.SPMV_AUTO, 0)]
+            (smb.SPMV_VECTOR, 32), (smb.SPMV_STREAM, 0), (smb.SPMV_STREAM_TMA, 0), (smb.SPMV_BANDED, 0), (smb.SPMV_STREAM_PIPE, 0), (smb.SPMV_RING, 0), (smb.SPMV_AUTO, 0)]
 
 
 def _check(smb, orc, ctx, case, seed=11, x_extra=0):
@@ -118,12 +118,45 @@ def test_host_buffer_pipeline_chunks(smb, orc, ctx, chunks, monkeypatch):
         assert np.array_equal(a.mvp_host(hx, hy), orc.mvp(vals, cols, offs, x))
 
 
+@pytest.mark.parametrize("vdt,idt", COMBOS)
+def test_ring_kernel_windows_and_fallbacks(smb, orc, ctx, vdt, idt):
+    """RING stages everything by TMA, including up to four windows of x per block.  Stencils get windows; a short-row matrix
+    with scattered columns gets none (global gathers); a borrowed, misaligned x must not be bulk-copied; long rows fall back
+    to STREAM.  All bit-exact (storage-order sums)."""
+    for nx, ny, nz in [(40, 30, 1), (24, 20, 18)]:
+        vals, cols, offs = orc.laplace(vdt, idt, nx, ny, nz)
+        n = nx * ny * nz
+        a = smb.SparseMatCRS.from_raw_parts(ctx, n, n, vals, cols, offs).configure(smb.SPMV_RING)
+        info = a.plan_info()
+        assert info["variant"] == smb.SPMV_RING and info["n_xwin_blocks"] == info["n_blocks"]   # every block got its windows
+        x = orc.uniform(vdt, 21, n)
+        want = orc.mvp(vals, cols, offs, x)
+        xd = smb.DenseVec.from_vec(ctx, x)
+        assert np.array_equal(a.mvp(xd).to_numpy(), want)
+        # borrowed device memory, 4 or 8 bytes off 16-byte alignment, no padding behind it: same bits
+        big = smb.DenseVec.from_vec(ctx, np.concatenate([[0], x]).astype(vdt))
+        xw = smb.DenseVec.wrap(ctx, big.device_ptr() + np.dtype(vdt).itemsize, n, vdt)
+        assert np.array_equal(a.mvp(xw).to_numpy(), want)
+        lhs = orc.uniform(vdt, 22, n)
+        got = a.inner_prod(smb.DenseVec.from_vec(ctx, lhs), xd)               # fused dot: weights staged by TMA too
+        ref = float(np.sum(lhs.astype(np.float64) * want.astype(np.float64)))
+        assert abs(float(got) - ref) <= 1e-5 * float(np.sum(np.abs(lhs.astype(np.float64) * want.astype(np.float64))))
+    case = cases.ragged(41, 6000, 900_000, 9, vdt, idt)                        # scattered columns: no windows
+    a = smb.SparseMatCRS.from_raw_parts(ctx, *case).configure(smb.SPMV_RING)
+    assert a.plan_info()["variant"] == smb.SPMV_RING and a.plan_info()["n_xwin_blocks"] == 0
+    x = np.random.default_rng(1).uniform(-1, 1, case[1]).astype(vdt)
+    assert np.array_equal(a.mvp(smb.DenseVec.from_vec(ctx, x)).to_numpy(), orc.mvp(case[2], case[3], case[4], x))
+    long_rows = cases.ragged(42, 300, 5000, 90, vdt, idt)                      # rows > 32 entries: not RING's business
+    a = smb.SparseMatCRS.from_raw_parts(ctx, *long_rows).configure(smb.SPMV_RING)
+    assert a.plan_info()["variant"] == smb.SPMV_STREAM
+
+
 def test_reference_known_answers(smb, ctx):
     """lib.rs:80-82 (34.544, storage order [col1, col2, col0]) and lib.rs:150-152 (20.16), f32, assert_eq!."""
     a = smb.SparseMatCRS.from_raw_parts(ctx, 3, 3, np.array([4.2, 0.12, 7.12, 4.12, 2.24, 2.12], F32),
                                         np.array([1, 2, 0, 2, 1, 2], U32), np.array([0, 3, 5, 6], U32))
     v = smb.DenseVec.from_vec(ctx, np.array([2.0, 4.8, 1.2], F32))
-    for variant in (smb.SPMV_AUTO, smb.SPMV_SCALAR, smb.SPMV_STREAM, smb.SPMV_STREAM_TMA, smb.SPMV_BANDED, smb.SPMV_STREAM_PIPE):
+    for variant in (smb.SPMV_AUTO, smb.SPMV_SCALAR, smb.SPMV_STREAM, smb.SPMV_STREAM_TMA, smb.SPMV_BANDED, smb.SPMV_STREAM_PIPE, smb.SPMV_RING):
         a.configure(variant)
         assert (a * v).get(0) == F32(34.544)
     assert a.density() == 6.0 / 9.0                                        # lib.rs:83
@@ -175,7 +208,7 @@ def test_full_size_headline_workload_properties(smb, ctx):
     x = smb.DenseVec(ctx, n ** 3, F32)
     x.fill_uniform(2)
     ref = None
-    for variant in (smb.SPMV_STREAM, smb.SPMV_STREAM_TMA, smb.SPMV_STREAM_PIPE, smb.SPMV_SCALAR, smb.SPMV_AUTO):
+    for variant in (smb.SPMV_STREAM, smb.SPMV_STREAM_TMA, smb.SPMV_STREAM_PIPE, smb.SPMV_RING, smb.SPMV_SCALAR, smb.SPMV_AUTO):
         a.configure(variant)
         got = a.mvp(x).to_numpy()
         if ref is None:
