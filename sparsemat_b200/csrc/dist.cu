@@ -114,6 +114,7 @@ static smb200_status dist_build_plans(smb200_dist* d) {
     SMB_TRY(plan_build_range(m, d->plan_int, m->want_variant, m->want_lanes, m->want_flags, d->int_begin, d->int_end));
     SMB_TRY(plan_build_range(m, d->plan_lo, m->want_variant, m->want_lanes, m->want_flags, 0, d->int_begin));
     SMB_TRY(plan_build_range(m, d->plan_hi, m->want_variant, m->want_lanes, m->want_flags, d->int_end, d->n_local));
+    if (!m->plan.built && m->n_rows) SMB_TRY(plan_build(m));          // whole local block: used when the halo is awaited first
     return SMB200_OK;
 }
 
@@ -165,8 +166,21 @@ static smb200_status dist_spmv_impl(smb200_dist* d, void* x, void* y, double* S)
     SMB_TRY(dist_exchange_begin(d, x));
     // Boundary rows: queued on the (high-priority) side stream right behind the halo receive, so they run as soon
     // as the ghosts have landed, in between the waves of the interior kernel, instead of after it.
-    static const bool overlap = []{ const char* e = getenv("SMB200_DIST_OVERLAP"); return !(e && e[0] == '0'); }();
-    if (exchange && !overlap) {                 // debugging aid: boundary rows on the main stream after the interior
+    // Two schedules.  Non-persistent interior kernels (many small CTAs): the boundary launches ride the high-priority side
+    // stream and slip in between the interior's waves.  Persistent ring interior (it holds every SM until it is done, so a
+    // concurrent kernel only perturbs it — measured 298 us vs 269 us on 2 GPUs): boundary rows follow on the main stream.
+    static const int overlap_env = []{ const char* e = getenv("SMB200_DIST_OVERLAP"); return e ? (e[0] == '0' ? 0 : 1) : -1; }();
+    const bool overlap = overlap_env >= 0 ? overlap_env == 1 : d->plan_int.variant != SMB200_SPMV_RING;
+    if (exchange && !overlap && m->plan.built && m->plan.variant == SMB200_SPMV_RING) {
+        // Persistent ring: it owns every SM until it is done, and a NCCL send/recv kernel that arrives meanwhile finds no SM
+        // to run on (measured: the exchange then completes only after the interior, +60 us on ranks with two neighbours).
+        // So: halo first (~20 us over NVLink), then ONE launch over all local rows.
+        SMB_CUDA(cudaEventRecord(ctx->ev_b, ctx->aux_stream));
+        SMB_TRY(dist_exchange_end(d));
+        if (S) return spmv_launch_cg(m, m->plan, 0, d->n_local, x, y, x, S, 0, true);
+        return spmv_launch_plan(m, m->plan, 0, d->n_local, x, y, nullptr, 0);
+    }
+    if (exchange && !overlap) {
         SMB_CUDA(cudaEventRecord(ctx->ev_b, ctx->aux_stream));
         if (S) SMB_TRY(spmv_launch_cg(m, d->plan_int, d->int_begin, d->int_end, x, y, x, S, 0, true));
         else SMB_TRY(spmv_launch_plan(m, d->plan_int, d->int_begin, d->int_end, x, y, nullptr, 0));
@@ -204,8 +218,10 @@ static smb200_status dist_spmv_impl(smb200_dist* d, void* x, void* y, double* S)
     g_redirect = LaunchRedirect();
     SMB_TRY(st);
     if (exchange) SMB_CUDA(cudaEventRecord(ctx->ev_b, ctx->aux_stream));
-    if (S) SMB_TRY(spmv_launch_cg(m, d->plan_int, d->int_begin, d->int_end, x, y, x, S, 0, true));
-    else SMB_TRY(spmv_launch_plan(m, d->plan_int, d->int_begin, d->int_end, x, y, nullptr, 0));
+    if (S) st = spmv_launch_cg(m, d->plan_int, d->int_begin, d->int_end, x, y, x, S, 0, true);
+    else st = spmv_launch_plan(m, d->plan_int, d->int_begin, d->int_end, x, y, nullptr, 0);
+    g_redirect = LaunchRedirect();
+    SMB_TRY(st);
     SMB_TRY(dist_exchange_end(d));
     return SMB200_OK;
 }
