@@ -88,6 +88,8 @@ class ClockSampler:
 
     def _once(self):
         nv = self.nv
+        if nv is None:
+            return
         try:
             self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
             r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
@@ -252,6 +254,7 @@ def run_ours(args):
         for _ in range(args.steps):
             step()
         ev1.record()
+        clk._once()                    # the K launches are queued and running: one sample from this thread for certain
         ms = ev0.elapsed_ms(ev1)
         barrier()
     launches = smb.api.lib.smb200_launch_count() - launches0
