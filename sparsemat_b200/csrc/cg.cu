@@ -268,7 +268,10 @@ smb200_status smb200_cg_solve(smb200_crs* a, const smb200_vec* b, smb200_vec* x,
     memcpy(w.scalars_host + 3 * S_COUNT, init, sizeof init);
     SMB_CUDA(cudaMemcpyAsync(w.scalars, w.scalars_host + 3 * S_COUNT, sizeof init, cudaMemcpyHostToDevice, ctx->stream));
     // r = b - A x ; p = r ; rr = r.r
-    SMB_TRY(spmv_launch_plan(a, a->plan, 0, n, x->d, w.ap, nullptr, 0));
+    g_x_unpadded = !x->owned;                                   // the start vector may be borrowed memory
+    const smb200_status st0 = spmv_launch_plan(a, a->plan, 0, n, x->d, w.ap, nullptr, 0);
+    g_x_unpadded = false;
+    SMB_TRY(st0);
     SMB_TRY(cg_init_launch(ctx, w, a->vt, b->d, n));
 
     const char* genv = getenv("SMB200_CG_GRAPH");

@@ -177,6 +177,9 @@ namespace smb {
 // the side stream (behind the halo receive) with their own partials buffer.
 struct LaunchRedirect { cudaStream_t stream = nullptr; double* partials = nullptr; };
 extern thread_local LaunchRedirect g_redirect;
+// Set while an SpMV reads a caller-owned (smb200_vec_wrap) vector: such memory has no padding behind its last element,
+// so kernels must not round bulk copies of it up to 16 bytes.
+extern thread_local bool g_x_unpadded;
 
 // implemented across the .cu files
 void ctx_retain(smb200_ctx* ctx);

@@ -1241,7 +1241,6 @@ smb200_status plan_build(smb200_crs* m) {
 }
 
 // ---- launch ---------------------------------------------------------------------------------------------
-static thread_local bool g_x_unpadded = false;        // smb200_spmv: x / w are caller-owned device memory without tail padding
 static thread_local unsigned g_last_pipe_grid = 0;   // CTAs of the most recent persistent launch (= its dot partials)
 
 template <class T, class I, bool DOT>
@@ -1604,7 +1603,10 @@ smb200_status smb200_bilinear(smb200_crs* a, const smb200_vec* lhs, const smb200
         SMB_TRY(dev_alloc(&ctx->stage_y, yb));
         ctx->stage_y_bytes = yb;
     }
-    SMB_TRY(spmv_launch(a, rhs->d, ctx->stage_y, lhs->d, 1));
+    g_x_unpadded = !rhs->owned;
+    const smb200_status st = spmv_launch(a, rhs->d, ctx->stage_y, lhs->d, 1);
+    g_x_unpadded = false;
+    SMB_TRY(st);
     return fetch_result(ctx, 1, out);
 }
 

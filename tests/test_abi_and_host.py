@@ -143,3 +143,20 @@ def test_ghost_plan_simulated_ranks(smb, orc, idt):
             assert np.array_equal(orc.mvp(lv, local_cols, lofs, x_local), want[lo:hi])
     with pytest.raises(smb.SmbError):                                      # a column outside the global matrix
         smb.ghost_plan(np.array([5000], idt), 2, 0, smb.partition_rows(n_rows, 2))
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """bench.py --impl reference (the oracle port on the host cores) honours the bench contract: exactly one JSON line on
+    stdout with the metric / config / cpu_baseline / e2e keys.  Runs the full C2 workload on the CPU (a few seconds)."""
+    import json
+    import sys
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "3", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [l for l in res.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "crs_spmv_effective_hbm_gbs" and d["unit"] == "GB/s" and d["higher_is_better"]
+    assert d["value"] > 0 and d["config"]["nnz"] == 117_047_296 and d["dtype"] == "f32"
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["serial_value"] > 0
+    assert d["e2e"] == {"value": d["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
