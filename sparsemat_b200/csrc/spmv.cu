@@ -1514,7 +1514,8 @@ smb200_status smb200_spmv_host(smb200_crs* a, const void* x_host, uint64_t nx, v
     HostPipe& hp = a->hp;
     if (!hp.built) {
         int chunks = env_int("SMB200_HOST_CHUNKS", 0);
-        if (chunks <= 0) chunks = (int)((a->n_rows + 524287) / 524288);
+        // ~8 MiB of y per chunk: measured best on C2 (8 chunks: 1.87 ms/step; 32: 2.22; 1: 2.60 — every piece costs ~10 us)
+        if (chunks <= 0) chunks = (int)((yb + (8u << 20) - 1) / (8u << 20));
         if (chunks > 64) chunks = 64;
         if (chunks < 1 || env_int("SMB200_HOST_PIPE", 1) == 0) chunks = 1;
         hp.n_chunks = chunks;
