@@ -56,6 +56,11 @@ def main():
                 "", "| kernel | launches | total us | mean us | share |", "|---|---:|---:|---:|---:|"]
         for name, v in sorted(per.items(), key=lambda kv: -sum(kv[1])):
             out.append(f"| `{name}` | {len(v)} | {sum(v):.1f} | {sum(v) / len(v):.2f} | {100 * sum(v) / total:.1f}% |")
+        top = max(per.items(), key=lambda kv: sum(kv[1]))
+        big = [v for v in top[1] if v > 0.5 * max(top[1])]
+        out += ["", f"`{top[0]}`: {len(big)} whole-matrix launches (the warm-up + timed steps of the bench), mean {sum(big) / len(big):.1f} us each; "
+                    f"the other {len(top[1]) - len(big)} launches are the row chunks of the host-buffer (e2e) path and per-chunk plan kernels. "
+                    "Inside the timed region the step IS this one launch (share 100 %)."]
         out.append("")
     if os.path.exists(rep):
         raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
