@@ -499,21 +499,113 @@ class ConjugateGradient:
 
 # ---- partition contract + multi-GPU ---------------------------------------------------------------------------
 class SparseMatPar:
-    """sparsemat_par.rs:12-35: the 1-D row-block contract (R = max_n_rows / n_blocks)."""
+    """sparsemat_par.rs:12-140: 1-D row blocks of R = max_n_rows / n_blocks rows, each a SparseMatIndexList with LOCAL
+    row ids and GLOBAL column ids, assembled on the host like the reference.  ``mvp`` is the reference's commented-out
+    ``mvp_par`` (sparsemat_par.rs:37-68) completed on the GPU: every block is converted by ``to_crs`` on the device and
+    multiplied against the shared x; block b writes y[b*R ..).  The reference's quirks are kept: the block id is clamped
+    to n_blocks (not n_blocks - 1), so rows >= n_blocks*R panic, and R == 0 divides by zero."""
 
-    def __init__(self, n_blocks: int, max_n_rows: int):
+    def __init__(self, n_blocks: int, max_n_rows: int, dtype=np.float64, itype=np.uint32):
+        if n_blocks == 0:
+            raise Panic("attempt to divide by zero")                      # sparsemat_par.rs:21
         self.n_blocks, self.max_n_rows = n_blocks, max_n_rows
+        self.n_rows_sub_matrix = max_n_rows // n_blocks
+        self.dtype, self.itype = np.dtype(dtype), np.dtype(itype)
+        self.sub_matrices = [SparseMatIndexList(dtype, itype) for _ in range(n_blocks)]
+        self._device = None                                               # (ctx, [SparseMatCRS per block]) after to_device
 
     @classmethod
-    def with_sub_matrices(cls, n_blocks, max_n_rows):
-        return cls(n_blocks, max_n_rows)
+    def with_sub_matrices(cls, n_blocks, max_n_rows, dtype=np.float64, itype=np.uint32):
+        return cls(n_blocks, max_n_rows, dtype, itype)
 
-    def get_block_and_row_id(self, row: int):
+    @classmethod
+    def with_capacity(cls, cap, dtype=np.float64, itype=np.uint32):      # sparsemat_par.rs:91-93
+        return cls(4, cap, dtype, itype)
+
+    def get_block_and_row_id(self, row: int):                             # sparsemat_par.rs:31-35
         b, r = C.c_uint64(), C.c_uint64()
         st = lib.smb200_par_locate(self.n_blocks, self.max_n_rows, row, C.byref(b), C.byref(r))
         if st != F.OK:
             raise Panic("attempt to divide by zero")
         return b.value, r.value
+
+    def _block(self, block_id: int) -> SparseMatIndexList:
+        if block_id >= len(self.sub_matrices):
+            raise Panic("index out of bounds")                            # Vec indexing with the clamped block id
+        return self.sub_matrices[block_id]
+
+    def _apply(self, i, j, v, op):
+        self._device = None
+        i = np.atleast_1d(np.asarray(i, np.uint64))
+        j = np.atleast_1d(np.asarray(j, np.uint64))
+        v = np.atleast_1d(np.asarray(v, self.dtype))
+        if self.n_rows_sub_matrix == 0:
+            raise Panic("attempt to divide by zero")
+        blocks = np.minimum(i // np.uint64(self.n_rows_sub_matrix), np.uint64(self.n_blocks))
+        if np.any(blocks >= self.n_blocks):
+            raise Panic("index out of bounds")
+        # keep the caller's order inside every block (insertion order is what to_crs freezes)
+        for b in np.unique(blocks):
+            m = blocks == b
+            self.sub_matrices[int(b)]._apply(i[m] - b * np.uint64(self.n_rows_sub_matrix), j[m], v[m], op)
+
+    def set(self, i, j, val):
+        self._apply(i, j, val, 0)
+
+    def add_to(self, i, j, val):
+        self._apply(i, j, val, 1)
+
+    def get(self, i: int, j: int):
+        b, r = self.get_block_and_row_id(i)
+        return self._block(b).get(r, j)
+
+    def n_rows(self) -> int:                                              # sparsemat_par.rs:95-107
+        last = 0
+        for b, m in enumerate(self.sub_matrices):
+            if m.n_rows() == 0:
+                break
+            last = b
+        return last * self.n_rows_sub_matrix + self.sub_matrices[last].n_rows()
+
+    def n_cols(self) -> int:
+        return max(m.n_cols() for m in self.sub_matrices)
+
+    def n_non_zero_entries(self) -> int:
+        return sum(m.n_non_zero_entries() for m in self.sub_matrices)
+
+    def density(self) -> float:                                           # sparsematrix.rs:237-241
+        return float(self.n_non_zero_entries()) / float(self.n_rows() * self.n_cols())
+
+    def to_device(self, ctx: Context):
+        """to_crs() of every block on the GPU (bit-exact layout per block)."""
+        self._device = (ctx, [m.to_crs(ctx) for m in self.sub_matrices])
+        return self
+
+    def mvp(self, rhs: DenseVec) -> DenseVec:
+        """y = A x, block by block against the shared x (the `Arc<rhs>` of sparsemat_par.rs:40-42)."""
+        ctx = rhs.ctx
+        if self._device is None or self._device[0] is not ctx:
+            self.to_device(ctx)
+        n = self.n_rows()
+        y = DenseVec(ctx, n, self.dtype)
+        R = self.n_rows_sub_matrix
+        done = 0
+        for b, crs in enumerate(self._device[1]):
+            rows_b = crs.n_rows()
+            if rows_b == 0 or done >= n:
+                break
+            if b * R + rows_b < n and rows_b < R:
+                # the default mvp would call IndexList::iter_row past the block's last row (indexlist.rs:88)
+                raise Panic("index out of bounds")
+            view = DenseVec.wrap(ctx, y.device_ptr() + b * R * self.dtype.itemsize, rows_b, self.dtype)
+            crs.mvp(rhs, out=view)
+            done = b * R + rows_b
+        return y
+
+    def __mul__(self, rhs):
+        if isinstance(rhs, DenseVec):
+            return self.mvp(rhs)
+        return NotImplemented
 
 
 def partition_rows(n_rows: int, world: int, align: int = 1) -> np.ndarray:

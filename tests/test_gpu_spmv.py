@@ -168,6 +168,31 @@ def test_reference_known_answers(smb, ctx):
     assert b.iter_row(5) == []                                             # lib.rs:148-149: past the end -> empty
 
 
+def test_sparsemat_par_known_answer_and_blocked_product(smb, orc, ctx):
+    """lib.rs:180-202 (check_sparsemat_par): with_sub_matrices(4, 16), the indexlist script, mvp row 0 == 34.544, density
+    6/9 — through the completed mvp_par on the GPU; then a matrix that fills several blocks against the oracle."""
+    mp = smb.SparseMatPar.with_sub_matrices(4, 16, np.float32, np.uint32)
+    mp.add_to(0, 1, 4.2); mp.add_to(1, 2, 4.12); mp.add_to(2, 2, 2.12); mp.add_to(1, 1, 1.12)
+    mp.add_to(1, 1, 1.12); mp.add_to(0, 2, 0.12); mp.set(0, 0, 8.12); mp.set(0, 0, 7.12)
+    assert mp.get(0, 0) == F32(7.12) and mp.get(0, 1) == F32(4.2)
+    y = mp.mvp(smb.DenseVec.from_vec(ctx, np.array([2.0, 4.8, 1.2], F32)))
+    assert y.dim() == 3 and y.get(0) == F32(34.544)
+    assert mp.density() == 6.0 / 9.0
+    with pytest.raises(smb.Panic):                                         # row 16 -> block 4 of 4 (the clamp quirk)
+        mp.set(16, 0, 1.0)
+    # 4 blocks of 250 rows, every block full: equals the product of the assembled global matrix, bit for bit
+    n_rows, n_cols, vals, cols, offs = cases.ragged(51, 1000, 800, 12, F64, U32, empty_frac=0.0)
+    i = np.repeat(np.arange(n_rows), np.diff(offs.astype(np.int64)))
+    big = smb.SparseMatPar(4, 1000, F64, U32)
+    big.set(np.append(i, np.arange(0, 1000, 250) + 249), np.append(cols, [0, 0, 0, 0]), np.append(vals, [0.5, 0.5, 0.5, 0.5]))
+    ref = orc.IndexListMat(F64, U32)
+    ref.set(np.append(i, np.arange(0, 1000, 250) + 249), np.append(cols, [0, 0, 0, 0]), np.append(vals, [0.5, 0.5, 0.5, 0.5]))
+    _, _, wv, wc, wo = ref.to_crs()
+    x = orc.uniform(F64, 3, 800)
+    assert big.n_rows() == 1000 and big.n_non_zero_entries() == wv.size
+    assert np.array_equal(big.mvp(smb.DenseVec.from_vec(ctx, x)).to_numpy(), orc.mvp(wv, wc, wo, x))
+
+
 def test_dimension_mismatch_panics_like_the_reference(smb, ctx):
     a = smb.SparseMatCRS.laplace(ctx, F64, U32, 8, 8, 1)
     with pytest.raises(smb.Panic):                                         # rhs.get(col) out of bounds (densevec.rs:40-42)
