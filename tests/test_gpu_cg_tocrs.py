@@ -137,6 +137,14 @@ def test_cg_iter_max_and_panics(smb, ctx):
         smb.ConjugateGradient().solve(rect, smb.DenseVec(ctx, 2, np.float64), smb.DenseVec(ctx, 2, np.float64))
 
 
+def test_plain_c_client_of_the_abi():
+    """tests/c/abi_example.c: C99, include/smb200.h only — the reference's known answers through the raw C ABI."""
+    exe = os.path.join(ROOT, "build", "abi_example")
+    assert os.path.exists(exe), "build() did not produce build/abi_example"
+    res = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0 and "abi_example: ok" in res.stdout, res.stdout + res.stderr
+
+
 def test_cpp_host_mirror_replays_the_reference_tests():
     """tests/cpp/replay_reference_tests.cpp: lib.rs's hot-path tests written against the C++ mirror of the crate."""
     exe = os.path.join(ROOT, "build", "replay_reference_tests")

@@ -168,6 +168,37 @@ def test_reference_known_answers(smb, ctx):
     assert b.iter_row(5) == []                                             # lib.rs:148-149: past the end -> empty
 
 
+@pytest.mark.parametrize("seed", range(6))
+def test_ring_windows_on_random_multi_diagonal_matrices(smb, orc, ctx, seed):
+    """Randomised: 1-9 diagonals at random offsets (clustered or far apart, so blocks need 1..>4 windows; beyond four the block
+    gathers from global memory), ragged ends, rectangular shapes, all type combinations, unsorted entries inside a row."""
+    rng = np.random.default_rng(1000 + seed)
+    vdt, idt = COMBOS[seed % 4]
+    n_rows = int(rng.integers(3000, 60000))
+    n_cols = int(n_rows * rng.uniform(0.7, 1.6))
+    ndiag = int(rng.integers(1, 10))
+    offsets = np.unique(np.concatenate([[0], rng.integers(-n_cols // 2, n_cols // 2, ndiag - 1) if ndiag > 1 else []]).astype(np.int64))
+    if seed % 2:                                                           # clusters of neighbouring diagonals
+        offsets = np.unique(np.concatenate([offsets, offsets + 1, offsets - 1]))
+    rows = np.repeat(np.arange(n_rows, dtype=np.int64), offsets.size)
+    cols = rows * n_cols // n_rows + np.tile(offsets, n_rows)
+    keep = (cols >= 0) & (cols < n_cols) & (rng.random(cols.size) > 0.05)
+    rows, cols = rows[keep], cols[keep]
+    perm = np.lexsort((rng.random(rows.size), rows))                       # shuffle inside each row
+    rows, cols = rows[perm], cols[perm]
+    offs = np.zeros(n_rows + 1, np.int64)
+    np.cumsum(np.bincount(rows, minlength=n_rows), out=offs[1:])
+    vals = rng.uniform(-1, 1, cols.size).astype(vdt)
+    a = smb.SparseMatCRS.from_raw_parts(ctx, n_rows, n_cols, vals, cols.astype(idt), offs.astype(idt)).configure(smb.SPMV_RING)
+    info = a.plan_info()
+    assert info["variant"] == smb.SPMV_RING
+    x = rng.uniform(-1, 1, n_cols).astype(vdt)
+    want = orc.mvp(vals, cols.astype(idt), offs.astype(idt), x)
+    assert np.array_equal(a.mvp(smb.DenseVec.from_vec(ctx, x)).to_numpy(), want), (seed, info)
+    a.configure(smb.SPMV_AUTO)
+    assert np.array_equal(a.mvp(smb.DenseVec.from_vec(ctx, x)).to_numpy(), want), (seed, a.plan_info())
+
+
 def test_sparsemat_par_known_answer_and_blocked_product(smb, orc, ctx):
     """lib.rs:180-202 (check_sparsemat_par): with_sub_matrices(4, 16), the indexlist script, mvp row 0 == 34.544, density
     6/9 — through the completed mvp_par on the GPU; then a matrix that fills several blocks against the oracle."""
