@@ -54,7 +54,8 @@ def _built():
     """The product library and the oracle are built in-tree; build them if a fresh checkout lacks them."""
     lib = os.path.join(ROOT, "sparsemat_b200", "lib", "libsmb200.so")
     orc = os.path.join(ROOT, "oracle", "liboracle.so")
-    if not (os.path.exists(lib) and os.path.exists(orc)):
+    bins = [os.path.join(ROOT, "build", "replay_reference_tests"), os.path.join(ROOT, "build", "abi_example")]
+    if not (os.path.exists(lib) and os.path.exists(orc) and all(os.path.exists(b) for b in bins)):
         import __graft_entry__ as ge
         ge.build()
 
