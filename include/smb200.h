@@ -48,7 +48,8 @@ enum {
 typedef enum { SMB200_F32 = 0, SMB200_F64 = 1 } smb200_vtype;   /* types.rs:70-77 */
 typedef enum { SMB200_U32 = 0, SMB200_U64 = 1 } smb200_itype;   /* types.rs:48-49 */
 
-/* SpMV kernel families.  AUTO picks from the row-length statistics. */
+/* SpMV kernel families.  AUTO picks from the row-length statistics and, for short rows, from
+ * the column structure. */
 typedef enum {
     SMB200_SPMV_AUTO = 0,
     SMB200_SPMV_SCALAR = 1,  /* one thread per row, storage-order sum (bit-exact vs the reference)   */
@@ -61,10 +62,12 @@ typedef enum {
                                 multi-stage shared-memory ring filled by cp.async.bulk (TMA) + mbarrier,
                                 so the HBM stream never waits for the gather / row-sum phases         */
     SMB200_SPMV_RING = 7     /* K4 persistent, short rows (<= 32 entries: stencils, FEM): values, columns, row
-                                offsets, the block's x segments (up to 4 windows found at plan time) and
-                                the dot weights are ALL staged by TMA into a shared-memory ring; no
-                                synchronous global load is left in the loop.  Falls back to STREAM when
-                                the matrix has longer rows                                            */
+                                offsets and the block's x segments (up to 4 windows found at plan time) are
+                                ALL staged by TMA into a shared-memory ring by a producer warp; consumer warps
+                                sum one row per thread in storage order (bit-exact) with no block barrier.
+                                Blocks without windows gather x from global memory.  Falls back to STREAM
+                                when the matrix has longer rows.  AUTO picks it when >= 80 % of the blocks
+                                have windows                                                           */
 } smb200_spmv_variant;
 
 /* flags for smb200_crs_configure */
