@@ -117,7 +117,11 @@ struct SpmvPlan {
     unsigned long long* seg_lo = nullptr; // RING: [4 * n_blocks] first column of each x segment of the block (aligned down)
     unsigned* seg_len = nullptr;        // RING: [4 * n_blocks] segment lengths in elements (0 = unused; all 0 = no window)
     unsigned ocap = 0, xcap = 0;        // RING: row-offset / x-window capacity of a stage (elements)
+    unsigned colb = 0;                  // RING: bytes per element of a stage's column area (2 = packed: every block compressed)
     uint64_t n_xwin = 0;                // RING: blocks whose columns fit <= 4 windows
+    uint16_t* lcols = nullptr;          // RING: 16-bit window-relative columns of the windowed blocks (index compression);
+    uint64_t lcols_base = 0;            //       lcols[k - lcols_base] belongs to non-zero k (lcols_base is a multiple of 8)
+    uint64_t n_c16 = 0;                 //       non-zeros whose column the kernel reads from lcols instead of `columns`
     unsigned cap = 0, target = 0;       // STREAM*: staging capacity / merge target the plan was cut for (elements)
     void* blk_win = nullptr;            // BANDED: [2*n_blocks] (cmin, cmax+1) per block, index type
     uint64_t max_win = 0;               // BANDED: widest window (elements)

@@ -702,7 +702,8 @@ struct RingDesc {
     unsigned long long r0, r1, a0, r0a;
     unsigned long long lo[kNSeg];            // first column of each window (unused: all ones)
     long long delta[kNSeg];                  // window element index = column + delta
-    unsigned xwin;                           // 1: the windows cover the block; 0: gather x from global memory
+    unsigned xwin;                           // number of windows that cover the block; 0: gather x from global memory
+    unsigned c16;                            // 1: the column area of the stage holds 16-bit indices into the staged windows
 };
 
 template <class T, class I, int NSEG> struct RingWin {
@@ -746,12 +747,34 @@ __device__ __forceinline__ double ring_rows(const T* sv, const I* sc, const I* s
     return acc;
 }
 
+// Same with compressed columns: the plan stored, for every non-zero of a windowed block, the 16-bit position of its
+// column inside the block's concatenated x windows, so a stage carries 2 bytes per column instead of sizeof(I) and the
+// consumer needs no window search.  The arithmetic (operands, order, roundings) is unchanged.
+template <class T, class I, bool DOT>
+__device__ __forceinline__ double ring_rows_c16(const T* sv, const uint16_t* sc, const I* so, const T* sx, const RingDesc& d,
+                                                unsigned lane_id, unsigned n_lanes, T* __restrict__ y, const T* __restrict__ w) {
+    const uint64_t r0 = d.r0, r1 = d.r1, a0 = d.a0, r0a = d.r0a;
+    double acc = 0.0;
+    for (uint64_t r = r0 + lane_id; r < r1; r += n_lanes) {
+        const unsigned ka = (unsigned)((uint64_t)so[r - r0a] - a0), ke = (unsigned)((uint64_t)so[r + 1 - r0a] - a0);
+        T wv = T(0);
+        if constexpr (DOT) wv = __ldg(w + r);
+        T sum = T(0);
+#pragma unroll 4
+        for (unsigned k = ka; k < ke; ++k) sum = add_rn(sum, mul_rn(sx[sc[k]], sv[k]));
+        y[r] = sum;
+        if constexpr (DOT) acc += (double)mul_rn(wv, sum);
+    }
+    return acc;
+}
+
 template <class T, class I, bool DOT>
 __global__ void __launch_bounds__(kRingThreads, 2)
 spmv_ring_kernel(const T* __restrict__ vals, const I* __restrict__ cols, const I* __restrict__ offs,
                  const I* __restrict__ blk_rows, const I* __restrict__ blk_nnz, const unsigned long long* __restrict__ seg_lo,
                  const unsigned* __restrict__ seg_len, unsigned n_blocks, unsigned cap, unsigned ocap, unsigned xcap,
-                 unsigned stages, int xwin_ok, const T* __restrict__ x, T* __restrict__ y, DotArgs dot) {
+                 unsigned colb, unsigned stages, int xwin_ok, const uint16_t* __restrict__ lcols, unsigned long long lcols_base,
+                 const T* __restrict__ x, T* __restrict__ y, DotArgs dot) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full[kPipeMaxStages];    // producer -> consumers: the stage's bytes have landed
     __shared__ __align__(8) uint64_t empty[kPipeMaxStages];   // consumers -> producer: every consumer warp has left the stage
@@ -760,7 +783,7 @@ spmv_ring_kernel(const T* __restrict__ vals, const I* __restrict__ cols, const I
     constexpr unsigned kConsumerWarps = kRingThreads / 32 - 1;
     const unsigned tid = threadIdx.x;
     const size_t o_cols = (size_t)cap * sizeof(T);
-    const size_t o_offs = o_cols + (size_t)cap * sizeof(I);
+    const size_t o_offs = o_cols + (size_t)cap * colb;          // colb = 2: every block of the plan streams 16-bit columns
     const size_t o_x = o_offs + (size_t)(ocap + 8) * sizeof(I);
     const size_t stage_bytes = o_x + (size_t)xcap * sizeof(T);
     double stop = 0.0;
@@ -787,8 +810,9 @@ spmv_ring_kernel(const T* __restrict__ vals, const I* __restrict__ cols, const I
                 if (j >= stages) mbar_wait(&empty[s], parity ^ 1u);     // the consumers have drained this stage's previous block
                 RingDesc& d = s_desc[s];
                 unsigned char* base = smem_raw + (size_t)s * stage_bytes;
-                const unsigned long long a0 = n0 & ~3ull, r0a = r0 & ~(unsigned long long)(OA - 1);
-                const unsigned count = (unsigned)(((n1 - a0) + 3ull) & ~3ull);
+                // slices start at a multiple of 8 elements: 16-byte aligned for 2-byte compressed columns as well
+                const unsigned long long a0 = n0 & ~7ull, r0a = r0 & ~(unsigned long long)(OA - 1);
+                const unsigned count = (unsigned)(((n1 - a0) + 7ull) & ~7ull);
                 const unsigned ocount = (unsigned)(((r1 + 1 - r0a) + (OA - 1)) & ~(unsigned long long)(OA - 1));
                 d.r0 = r0; d.r1 = r1; d.a0 = a0; d.r0a = r0a;
                 unsigned xtotal = 0, nseg = 0;
@@ -800,13 +824,17 @@ spmv_ring_kernel(const T* __restrict__ vals, const I* __restrict__ cols, const I
                     nseg += len[i] ? 1u : 0u;
                 }
                 const bool xw = xwin_ok && xtotal > 0;
+                const bool c16 = xw && lcols != nullptr;
                 d.xwin = xw ? nseg : 0u;
-                unsigned bytes = count * (unsigned)(sizeof(T) + sizeof(I)) + ocount * (unsigned)sizeof(I);
+                d.c16 = c16 ? 1u : 0u;
+                const unsigned cbytes = count * (c16 ? 2u : (unsigned)sizeof(I));
+                unsigned bytes = count * (unsigned)sizeof(T) + cbytes + ocount * (unsigned)sizeof(I);
                 if (xw) bytes += xtotal * (unsigned)sizeof(T);
                 mbar_expect_tx(&full[s], bytes);
                 if (count) {
                     bulk_g2s(base, vals + a0, count * (unsigned)sizeof(T), &full[s]);
-                    bulk_g2s(base + o_cols, cols + a0, count * (unsigned)sizeof(I), &full[s]);
+                    if (c16) bulk_g2s(base + o_cols, lcols + (a0 - lcols_base), cbytes, &full[s]);
+                    else bulk_g2s(base + o_cols, cols + a0, cbytes, &full[s]);
                 }
                 bulk_g2s(base + o_offs, offs + r0a, ocount * (unsigned)sizeof(I), &full[s]);
                 if (xw) {
@@ -831,7 +859,8 @@ spmv_ring_kernel(const T* __restrict__ vals, const I* __restrict__ cols, const I
             const I* so = reinterpret_cast<const I*>(base + o_offs);
             const T* sx = reinterpret_cast<const T*>(base + o_x);
             const T* w = (const T*)dot.w;
-            switch (d.xwin) {                     // number of x windows of the block (block-uniform)
+            if (d.c16) acc += ring_rows_c16<T, I, DOT>(sv, reinterpret_cast<const uint16_t*>(base + o_cols), so, sx, d, lane_id, n_lanes, y, w);
+            else switch (d.xwin) {                // number of x windows of the block (block-uniform)
                 case 0: acc += ring_rows<T, I, DOT, 0>(sv, sc, so, sx, d, lane_id, n_lanes, x, y, w); break;
                 case 1: acc += ring_rows<T, I, DOT, 1>(sv, sc, so, sx, d, lane_id, n_lanes, x, y, w); break;
                 case 2: acc += ring_rows<T, I, DOT, 2>(sv, sc, so, sx, d, lane_id, n_lanes, x, y, w); break;
@@ -921,6 +950,35 @@ block_segments_kernel(const I* __restrict__ cols, const I* __restrict__ blk_nnz,
         for (int i = 0; i < kNSeg; ++i) { seg_lo[kNSeg * b + i] = ok ? lo[i] : ~0ull; seg_len[kNSeg * b + i] = ok ? len[i] : 0u; }
         if (ok) atomicAdd(n_ok, 1ull);
     }
+}
+
+// Plan time, one CTA per block: index compression.  For a block with windows, the position of every column inside the
+// block's concatenated windows (the layout the producer stages them in) as a 16-bit number.
+template <class I>
+__global__ void __launch_bounds__(256)
+ring_compress_kernel(const I* __restrict__ cols, const I* __restrict__ blk_nnz, const unsigned long long* __restrict__ seg_lo,
+                     const unsigned* __restrict__ seg_len, unsigned long long lcols_base, uint16_t* __restrict__ lcols,
+                     unsigned long long* __restrict__ n_c16) {
+    const size_t b = blockIdx.x;
+    unsigned long long lo[kNSeg];
+    unsigned at[kNSeg], total = 0;
+#pragma unroll
+    for (int i = 0; i < kNSeg; ++i) {
+        const unsigned len = seg_len[kNSeg * b + i];
+        lo[i] = len ? seg_lo[kNSeg * b + i] : ~0ull;
+        at[i] = total;
+        total += len;
+    }
+    if (total == 0) return;                                   // no windows: the kernel reads the original columns
+    const uint64_t n0 = (uint64_t)blk_nnz[b], n1 = (uint64_t)blk_nnz[b + 1];
+    for (uint64_t k = n0 + threadIdx.x; k < n1; k += 256) {
+        const unsigned long long c = (unsigned long long)cols[k];
+        int i = 0;
+#pragma unroll
+        for (int j = 1; j < kNSeg; ++j) if (c >= lo[j]) i = j;
+        lcols[k - lcols_base] = (uint16_t)((unsigned)(c - lo[i]) + at[i]);
+    }
+    if (threadIdx.x == 0) atomicAdd(n_c16, (unsigned long long)(n1 - n0));
 }
 
 // ---- plan construction --------------------------------------------------------------------------------
@@ -1028,6 +1086,7 @@ void plan_free(SpmvPlan& p) {
     if (p.blk_flags) cudaFree(p.blk_flags);
     if (p.seg_lo) cudaFree(p.seg_lo);
     if (p.seg_len) cudaFree(p.seg_len);
+    if (p.lcols) cudaFree(p.lcols);
     if (p.blk_win) cudaFree(p.blk_win);
     p = SpmvPlan();
 }
@@ -1071,7 +1130,8 @@ static void stream_shape(const smb200_crs* m, int variant, unsigned* cap, unsign
     if (c < 256) c = 256;
     if (c > kMaxCap) c = kMaxCap;
     t = c - c / 9;                     // leave room for the row that straddles the target
-    if (variant == SMB200_SPMV_RING) t = c - (unsigned)kRowMajorMax - 8;   // rows are short: a block overshoots by < one row
+    // rows are short: a block overshoots the target by < one row, and its slice is widened to multiples of 8 elements
+    if (variant == SMB200_SPMV_RING) t = c - (unsigned)kRowMajorMax - 16;
     t = (unsigned)env_int("SMB200_STREAM_TARGET", (int)t);
     if (t + 8 > c) t = c - 8;
     *cap = c;
@@ -1104,6 +1164,162 @@ smb200_status plan_build_range(smb200_crs* m, SpmvPlan& p, int want_variant, int
         if (p.variant == SMB200_SPMV_RING && p.n_xwin * 10 >= p.n_blocks * 8) return SMB200_OK;
     }
     return plan_build_range_impl(m, p, want_variant, want_lanes, flags, rb, re);
+}
+
+// Cut rows [rb, re) into blocks of `target` merge units (key = row_weight * rows + non-zeros): blk_rows / blk_nnz.
+static smb200_status plan_cut(smb200_crs* m, SpmvPlan& p, uint64_t rb, uint64_t re, uint64_t ob, uint64_t oe, unsigned target,
+                              uint64_t row_weight) {
+    smb200_ctx* ctx = m->ctx;
+    const size_t is = isize(m->it);
+    if (p.blk_rows) { cudaFree(p.blk_rows); p.blk_rows = nullptr; }
+    if (p.blk_nnz) { cudaFree(p.blk_nnz); p.blk_nnz = nullptr; }
+    p.target = target;
+    const uint64_t merge_len = (re - rb) * row_weight + (oe - ob);
+    p.n_blocks = (merge_len + target - 1) / target;
+    if (p.n_blocks == 0) p.n_blocks = 1;
+    SMB_REQUIRE(p.n_blocks < 0x7FFFFFFFull, SMB200_ERR_UNSUPPORTED, "spmv: too many row blocks");
+    SMB_CUDA(cudaMalloc(&p.blk_rows, (p.n_blocks + 1) * is));
+    SMB_CUDA(cudaMalloc(&p.blk_nnz, (p.n_blocks + 1) * is));
+    const unsigned g = (unsigned)((p.n_blocks + 1 + 255) / 256);
+    if (m->it == SMB200_U64) split_rows_kernel<uint64_t><<<g, 256, 0, ctx->stream>>>((const uint64_t*)m->offsets, rb, re, target, row_weight, p.n_blocks, (uint64_t*)p.blk_rows, (uint64_t*)p.blk_nnz);
+    else split_rows_kernel<uint32_t><<<g, 256, 0, ctx->stream>>>((const uint32_t*)m->offsets, rb, re, target, row_weight, p.n_blocks, (uint32_t*)p.blk_rows, (uint32_t*)p.blk_nnz);
+    count_launch();
+    SMB_CUDA(cudaGetLastError());
+    return SMB200_OK;
+}
+
+// RING: the x windows of every block (<= p.xcap elements in total, else the block gets none) -> seg_lo / seg_len / n_xwin.
+static smb200_status ring_segments(smb200_crs* m, SpmvPlan& p) {
+    smb200_ctx* ctx = m->ctx;
+    if (p.seg_lo) { cudaFree(p.seg_lo); p.seg_lo = nullptr; }
+    if (p.seg_len) { cudaFree(p.seg_len); p.seg_len = nullptr; }
+    SMB_CUDA(cudaMalloc(&p.seg_lo, (size_t)kNSeg * p.n_blocks * sizeof(unsigned long long)));
+    SMB_CUDA(cudaMalloc(&p.seg_len, (size_t)kNSeg * p.n_blocks * sizeof(unsigned)));
+    unsigned long long* d_ok = nullptr;
+    SMB_CUDA(cudaMalloc(&d_ok, sizeof(unsigned long long)));
+    cudaMemsetAsync(d_ok, 0, sizeof(unsigned long long), ctx->stream);
+    unsigned shift = 6;                                     // >= 64 columns per bucket, <= 131072 buckets
+    while (((m->n_cols + ((1ull << shift) - 1)) >> shift) > (uint64_t)kSegWords * 32u) ++shift;
+    const unsigned xalign = (unsigned)(16 / vsize(m->vt));
+    if (m->nnz) {
+        if (m->it == SMB200_U64) block_segments_kernel<uint64_t><<<(unsigned)p.n_blocks, 128, 0, ctx->stream>>>((const uint64_t*)m->columns, (const uint64_t*)p.blk_nnz, shift, p.xcap, xalign, p.seg_lo, p.seg_len, d_ok);
+        else block_segments_kernel<uint32_t><<<(unsigned)p.n_blocks, 128, 0, ctx->stream>>>((const uint32_t*)m->columns, (const uint32_t*)p.blk_nnz, shift, p.xcap, xalign, p.seg_lo, p.seg_len, d_ok);
+        count_launch();
+    } else {
+        cudaMemsetAsync(p.seg_len, 0, (size_t)kNSeg * p.n_blocks * sizeof(unsigned), ctx->stream);
+        cudaMemsetAsync(p.seg_lo, 0xff, (size_t)kNSeg * p.n_blocks * sizeof(unsigned long long), ctx->stream);
+    }
+    unsigned long long h_ok = 0;
+    cudaError_t e = cudaMemcpyAsync(&h_ok, d_ok, sizeof h_ok, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_ok);
+    SMB_CUDA(e);
+    p.n_xwin = h_ok;
+    return SMB200_OK;
+}
+
+// Largest slice (non-zeros, widened to multiples of 8 on both sides) and largest row count over the blocks of a cut.
+template <class I>
+__global__ void block_extent_kernel(const I* __restrict__ blk_rows, const I* __restrict__ blk_nnz, uint64_t n_blocks,
+                                    unsigned long long* __restrict__ out2) {
+    const uint64_t b = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    unsigned long long z = 0, r = 0;
+    if (b < n_blocks) {
+        const unsigned long long n0 = (unsigned long long)blk_nnz[b], n1 = (unsigned long long)blk_nnz[b + 1];
+        z = ((n1 + 7ull) & ~7ull) - (n0 & ~7ull);
+        r = (unsigned long long)blk_rows[b + 1] - (unsigned long long)blk_rows[b];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long z2 = __shfl_xor_sync(0xffffffffu, z, o), r2 = __shfl_xor_sync(0xffffffffu, r, o);
+        z = z2 > z ? z2 : z;
+        r = r2 > r ? r2 : r;
+    }
+    if ((threadIdx.x & 31) == 0) { atomicMax(out2, z); atomicMax(out2 + 1, r); }
+}
+
+constexpr size_t kRingStageBudget = 55 * 1024;   // two CTAs/SM x two stages (+ static shared memory) inside 227 KB
+
+// RING plan.  A stage holds [values cap*T][columns cap*colb][row offsets (ocap+8)*I][x windows xcap*T].
+//  (a) packed: every block windowed, columns staged as 16-bit window positions (colb = 2), capacities taken from the
+//      measured extents of the cut, the merge target grown until a stage is full — the bytes in flight per SM stay what
+//      they were with full-width columns although every non-zero now costs sizeof(I) - 2 bytes less;
+//  (b) conservative: worst-case capacities, full-width column area; blocks that did get windows still stream 16-bit
+//      columns (mixed), the others gather x from global memory.
+static smb200_status ring_plan(smb200_crs* m, SpmvPlan& p, uint64_t rb, uint64_t re, uint64_t ob, uint64_t oe, unsigned cap_b,
+                               unsigned target_b) {
+    smb200_ctx* ctx = m->ctx;
+    const size_t ts = vsize(m->vt), is = isize(m->it);
+    const uint64_t rows = re - rb, nnz = oe - ob;
+    const bool want_c16 = env_int("SMB200_RING_C16", 1) != 0;
+    bool packed = false;
+    if (want_c16 && nnz > 0 && env_int("SMB200_RING_PACK", 1) != 0 && getenv("SMB200_RING_CAP") == nullptr) {
+        const double mean = (double)nnz / (double)rows;
+        const double bytes_per_key = (mean * (double)(ts + 2) + (double)is) / (mean + 2.0);
+        double t = (double)env_int("SMB200_RING_FILL", 70) * 0.01 * (double)kRingStageBudget / bytes_per_key;
+        unsigned long long* d_ext = nullptr;
+        SMB_CUDA(cudaMalloc(&d_ext, 2 * sizeof(unsigned long long)));
+        for (int attempt = 0; attempt < 5 && !packed; ++attempt, t *= 0.9) {
+            if (t > 60000.0) t = 60000.0;
+            if (t < 512.0) break;
+            smb200_status st = plan_cut(m, p, rb, re, ob, oe, (unsigned)t & ~7u, 2);
+            if (st != SMB200_OK) { cudaFree(d_ext); return st; }
+            cudaMemsetAsync(d_ext, 0, 2 * sizeof(unsigned long long), ctx->stream);
+            const unsigned g = (unsigned)((p.n_blocks + 255) / 256);
+            if (m->it == SMB200_U64) block_extent_kernel<uint64_t><<<g, 256, 0, ctx->stream>>>((const uint64_t*)p.blk_rows, (const uint64_t*)p.blk_nnz, p.n_blocks, d_ext);
+            else block_extent_kernel<uint32_t><<<g, 256, 0, ctx->stream>>>((const uint32_t*)p.blk_rows, (const uint32_t*)p.blk_nnz, p.n_blocks, d_ext);
+            count_launch();
+            unsigned long long h_ext[2] = {0, 0};
+            cudaError_t e = cudaMemcpyAsync(h_ext, d_ext, sizeof h_ext, cudaMemcpyDeviceToHost, ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+            if (e != cudaSuccess) { cudaFree(d_ext); SMB_CUDA(e); }
+            const size_t cap = (size_t)((h_ext[0] + 7ull) & ~7ull), ocap = (size_t)((h_ext[1] + 3ull) & ~3ull);
+            const size_t fixed = cap * (ts + 2) + (ocap + 8) * is;
+            if (fixed + 64 * ts > kRingStageBudget) continue;
+            size_t xc = (kRingStageBudget - fixed) / ts;
+            if (xc > 65536) xc = 65536;
+            p.cap = (unsigned)cap;
+            p.ocap = (unsigned)ocap;
+            p.xcap = (unsigned)xc & ~3u;
+            st = ring_segments(m, p);
+            if (st != SMB200_OK) { cudaFree(d_ext); return st; }
+            packed = p.n_xwin == p.n_blocks;
+        }
+        cudaFree(d_ext);
+    }
+    p.colb = packed ? 2u : (unsigned)is;
+    if (!packed) {
+        p.cap = cap_b;
+        SMB_TRY(plan_cut(m, p, rb, re, ob, oe, target_b, 2));
+        // worst case of a cut with key = 2*rows + nnz: target/2 rows
+        p.ocap = (target_b / 2 + 8) & ~3u;
+        const size_t fixed = (size_t)cap_b * (ts + is) + (size_t)(p.ocap + 8) * is;
+        unsigned xc = kRingStageBudget > fixed ? (unsigned)((kRingStageBudget - fixed) / ts) : 0u;
+        if (xc > cap_b) xc = cap_b;
+        p.xcap = (unsigned)env_int("SMB200_RING_XCAP", (int)xc) & ~3u;
+        SMB_TRY(ring_segments(m, p));
+    }
+    // index compression: 16-bit window positions for the windowed blocks (the windows of one block hold <= xcap <= 65536
+    // elements).  Costs 2 bytes per non-zero of plan memory and saves sizeof(I) - 2 of every column read.
+    if (p.n_xwin > 0 && p.xcap <= 65536u && want_c16) {
+        p.lcols_base = ob & ~7ull;
+        const size_t n_l = (size_t)(oe - p.lcols_base) + 8;
+        SMB_CUDA(cudaMalloc(&p.lcols, n_l * sizeof(uint16_t) + kPadBytes));
+        unsigned long long* d_n = nullptr;
+        SMB_CUDA(cudaMalloc(&d_n, sizeof(unsigned long long)));
+        cudaMemsetAsync(d_n, 0, sizeof(unsigned long long), ctx->stream);
+        cudaMemsetAsync(p.lcols, 0, n_l * sizeof(uint16_t) + kPadBytes, ctx->stream);
+        if (m->it == SMB200_U64) ring_compress_kernel<uint64_t><<<(unsigned)p.n_blocks, 256, 0, ctx->stream>>>((const uint64_t*)m->columns, (const uint64_t*)p.blk_nnz, p.seg_lo, p.seg_len, p.lcols_base, p.lcols, d_n);
+        else ring_compress_kernel<uint32_t><<<(unsigned)p.n_blocks, 256, 0, ctx->stream>>>((const uint32_t*)m->columns, (const uint32_t*)p.blk_nnz, p.seg_lo, p.seg_len, p.lcols_base, p.lcols, d_n);
+        count_launch();
+        unsigned long long h_n = 0;
+        cudaError_t e2 = cudaMemcpyAsync(&h_n, d_n, sizeof h_n, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(ctx->stream);
+        cudaFree(d_n);
+        SMB_CUDA(e2);
+        p.n_c16 = h_n;
+    }
+    return SMB200_OK;
 }
 
 static smb200_status plan_build_range_impl(smb200_crs* m, SpmvPlan& p, int want_variant, int want_lanes, uint32_t flags,
@@ -1155,50 +1371,10 @@ static smb200_status plan_build_range_impl(smb200_crs* m, SpmvPlan& p, int want_
             SMB_CUDA(cudaStreamSynchronize(ctx->stream));
             ob = b32; oe = e32;
         }
-        // RING bounds the rows of a block as well (their offsets are staged): key = 2*rows + nnz
-        const uint64_t row_weight = variant == SMB200_SPMV_RING ? 2 : 1;
         if (variant == SMB200_SPMV_RING) {
-            // two CTAs/SM x two stages: (values + columns) + offsets + x windows of one stage <= ~56 KB
-            p.ocap = (target / 2 + 8) & ~3u;
-            const size_t budget = 55 * 1024, fixed = (size_t)cap * (vsize(m->vt) + isize(m->it)) + (size_t)(p.ocap + 8) * isize(m->it);
-            unsigned xc = budget > fixed ? (unsigned)((budget - fixed) / vsize(m->vt)) : 0u;
-            if (xc > cap) xc = cap;
-            p.xcap = (unsigned)env_int("SMB200_RING_XCAP", (int)xc) & ~3u;
-        }
-        const uint64_t merge_len = rows * row_weight + (oe - ob);
-        p.n_blocks = (merge_len + target - 1) / target;
-        if (p.n_blocks == 0) p.n_blocks = 1;
-        SMB_REQUIRE(p.n_blocks < 0x7FFFFFFFull, SMB200_ERR_UNSUPPORTED, "spmv: too many row blocks");
-        SMB_CUDA(cudaMalloc(&p.blk_rows, (p.n_blocks + 1) * is));
-        SMB_CUDA(cudaMalloc(&p.blk_nnz, (p.n_blocks + 1) * is));
-        const unsigned g = (unsigned)((p.n_blocks + 1 + 255) / 256);
-        if (m->it == SMB200_U64) split_rows_kernel<uint64_t><<<g, 256, 0, ctx->stream>>>((const uint64_t*)m->offsets, rb, re, target, row_weight, p.n_blocks, (uint64_t*)p.blk_rows, (uint64_t*)p.blk_nnz);
-        else split_rows_kernel<uint32_t><<<g, 256, 0, ctx->stream>>>((const uint32_t*)m->offsets, rb, re, target, row_weight, p.n_blocks, (uint32_t*)p.blk_rows, (uint32_t*)p.blk_nnz);
-        count_launch();
-        SMB_CUDA(cudaGetLastError());
-        if (variant == SMB200_SPMV_RING) {
-            SMB_CUDA(cudaMalloc(&p.seg_lo, (size_t)kNSeg * p.n_blocks * sizeof(unsigned long long)));
-            SMB_CUDA(cudaMalloc(&p.seg_len, (size_t)kNSeg * p.n_blocks * sizeof(unsigned)));
-            unsigned long long* d_ok = nullptr;
-            SMB_CUDA(cudaMalloc(&d_ok, sizeof(unsigned long long)));
-            cudaMemsetAsync(d_ok, 0, sizeof(unsigned long long), ctx->stream);
-            unsigned shift = 6;                                     // >= 64 columns per bucket, <= 131072 buckets
-            while (((m->n_cols + ((1ull << shift) - 1)) >> shift) > (uint64_t)kSegWords * 32u) ++shift;
-            const unsigned xalign = (unsigned)(16 / vsize(m->vt));
-            if (m->nnz) {
-                if (m->it == SMB200_U64) block_segments_kernel<uint64_t><<<(unsigned)p.n_blocks, 128, 0, ctx->stream>>>((const uint64_t*)m->columns, (const uint64_t*)p.blk_nnz, shift, p.xcap, xalign, p.seg_lo, p.seg_len, d_ok);
-                else block_segments_kernel<uint32_t><<<(unsigned)p.n_blocks, 128, 0, ctx->stream>>>((const uint32_t*)m->columns, (const uint32_t*)p.blk_nnz, shift, p.xcap, xalign, p.seg_lo, p.seg_len, d_ok);
-                count_launch();
-            } else {
-                cudaMemsetAsync(p.seg_len, 0, (size_t)kNSeg * p.n_blocks * sizeof(unsigned), ctx->stream);
-                cudaMemsetAsync(p.seg_lo, 0xff, (size_t)kNSeg * p.n_blocks * sizeof(unsigned long long), ctx->stream);
-            }
-            unsigned long long h_ok = 0;
-            cudaError_t e = cudaMemcpyAsync(&h_ok, d_ok, sizeof h_ok, cudaMemcpyDeviceToHost, ctx->stream);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-            cudaFree(d_ok);
-            SMB_CUDA(e);
-            p.n_xwin = h_ok;
+            SMB_TRY(ring_plan(m, p, rb, re, ob, oe, cap, target));
+        } else {
+            SMB_TRY(plan_cut(m, p, rb, re, ob, oe, target, 1));
         }
         if (variant == SMB200_SPMV_STREAM_PIPE) {
             SMB_CUDA(cudaMalloc(&p.blk_flags, p.n_blocks));
@@ -1274,7 +1450,12 @@ static smb200_status launch_typed(smb200_crs* m, const SpmvPlan& p, uint64_t rb,
             if (carve >= 0) SMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
             kern<<<(unsigned)p.n_blocks, kSpmvThreads, smem, st>>>(vals, cols, offs, (const I*)p.blk_rows, (const I*)p.blk_nnz, sh.cap, xx, yy, dot);
         } else if (p.variant == SMB200_SPMV_RING) {
-            const size_t stage = (size_t)sh.cap * (sizeof(T) + sizeof(I)) + (size_t)(p.ocap + 8) * sizeof(I) + (size_t)p.xcap * sizeof(T);
+            // bulk copies need 16-byte aligned sources whose rounded-up tails stay inside the allocation
+            const int xwin_ok = (((uintptr_t)x & 15u) == 0 && !g_x_unpadded && env_int("SMB200_RING_XWIN", 1) != 0) ? 1 : 0;
+            // without windows (borrowed, unpadded x) every block stages its full-width columns and no x
+            const unsigned colb = (xwin_ok && p.colb == 2) ? 2u : (unsigned)sizeof(I);
+            const unsigned xcap = xwin_ok ? p.xcap : 0u;
+            const size_t stage = (size_t)sh.cap * (sizeof(T) + colb) + (size_t)(p.ocap + 8) * sizeof(I) + (size_t)xcap * sizeof(T);
             // two CTAs per SM, two stages each: one block is consumed while the next one lands, and the second CTA's
             // consumers fill the issue slots the first one leaves idle
             int ctas = env_int("SMB200_RING_CTAS", 2);
@@ -1296,10 +1477,9 @@ static smb200_status launch_typed(smb200_crs* m, const SpmvPlan& p, uint64_t rb,
             uint64_t grid = (uint64_t)ctx->sm_count * (uint64_t)resident;
             if (grid > p.n_blocks) grid = p.n_blocks;
             g_last_pipe_grid = (unsigned)grid;
-            // bulk copies need 16-byte aligned sources whose rounded-up tails stay inside the allocation
-            const int xwin_ok = (((uintptr_t)x & 15u) == 0 && !g_x_unpadded && env_int("SMB200_RING_XWIN", 1) != 0) ? 1 : 0;
             kern<<<(unsigned)grid, kRingThreads, smem, st>>>(vals, cols, offs, (const I*)p.blk_rows, (const I*)p.blk_nnz, p.seg_lo, p.seg_len,
-                                                           (unsigned)p.n_blocks, sh.cap, p.ocap, p.xcap, (unsigned)stages, xwin_ok, xx, yy, dot);
+                                                           (unsigned)p.n_blocks, sh.cap, p.ocap, xcap, colb, (unsigned)stages, xwin_ok,
+                                                           xwin_ok ? p.lcols : nullptr, (unsigned long long)p.lcols_base, xx, yy, dot);
         } else if (p.variant == SMB200_SPMV_STREAM_PIPE) {
             int stages = env_int("SMB200_PIPE_STAGES", 3);
             if (stages < 3) stages = 3;     // the kernel reads the descriptor of block i + 1 during iteration i
@@ -1472,6 +1652,8 @@ smb200_status smb200_crs_plan_info(const smb200_crs* cm, smb200_plan_info* out) 
                              m->n_cols * vsize(m->vt) + m->n_rows * vsize(m->vt);
     out->launches_per_spmv = 1;
     out->n_xwin_blocks = m->plan.n_xwin;
+    out->nnz_c16 = m->plan.n_c16;
+    out->stream_bytes = out->algorithmic_bytes - m->plan.n_c16 * (isize(m->it) - 2);
     return SMB200_OK;
 }
 
@@ -1514,16 +1696,21 @@ smb200_status smb200_spmv_host(smb200_crs* a, const void* x_host, uint64_t nx, v
     HostPipe& hp = a->hp;
     if (!hp.built) {
         int chunks = env_int("SMB200_HOST_CHUNKS", 0);
-        // ~8 MiB of y per chunk: measured best on C2 (8 chunks: 1.87 ms/step; 32: 2.22; 1: 2.60 — every piece costs ~10 us)
-        if (chunks <= 0) chunks = (int)((yb + (8u << 20) - 1) / (8u << 20));
+        // ~8 MiB of y per chunk (measured best on C2: every chunk costs ~14 us of launches, events and copy set-up); the
+        // first and the last chunk are half as large: the upload of the first piece is the head of the pipeline (nothing
+        // else can run yet) and the download of the last slice its tail
+        if (chunks <= 0) { chunks = (int)((yb + (8u << 20) - 1) / (8u << 20)); if (chunks >= 4) ++chunks; }
         if (chunks > 64) chunks = 64;
         if (chunks < 1 || env_int("SMB200_HOST_PIPE", 1) == 0) chunks = 1;
         hp.n_chunks = chunks;
         hp.row_bounds.assign(chunks + 1, a->n_rows);
         hp.x_bounds.assign(chunks + 1, a->n_cols);
+        const bool taper = chunks >= 4 && env_int("SMB200_HOST_TAPER", 1) != 0;
+        const uint64_t units = taper ? 2 * (uint64_t)chunks - 2 : (uint64_t)chunks;     // weights 1,2,2,...,2,1
         for (int c = 0; c < chunks; ++c) {
-            hp.row_bounds[c] = ((a->n_rows * (uint64_t)c / (uint64_t)chunks) + 1023) / 1024 * 1024;
-            hp.x_bounds[c] = ((a->n_cols * (uint64_t)c / (uint64_t)chunks) + 1023) / 1024 * 1024;
+            const uint64_t at = taper ? (c == 0 ? 0 : 2 * (uint64_t)c - 1) : (uint64_t)c;
+            hp.row_bounds[c] = ((a->n_rows * at / units) + 1023) / 1024 * 1024;
+            hp.x_bounds[c] = ((a->n_cols * at / units) + 1023) / 1024 * 1024;
             if (hp.row_bounds[c] > a->n_rows) hp.row_bounds[c] = a->n_rows;
             if (hp.x_bounds[c] > a->n_cols) hp.x_bounds[c] = a->n_cols;
         }
@@ -1548,14 +1735,16 @@ smb200_status smb200_spmv_host(smb200_crs* a, const void* x_host, uint64_t nx, v
             if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
             cudaFree(d_rng);
             SMB_CUDA(e);
+            // Piece k of x ends where chunk k's columns end (rounded up, monotone), so chunk k waits for piece k only: for a
+            // banded matrix that is its own rows plus the band, and the product starts one piece — not two — into the upload.
+            // (Scattered columns: chunk 0 reaches the end of x, piece 0 is all of x, the later pieces are empty.)
             for (int c = 0; c < chunks; ++c) {
-                const unsigned long long mx = h_rng[2 * c + 1];           // max column + 1 (0: the chunk has no entries)
-                int piece = 0;
-                while (piece + 1 < chunks && hp.x_bounds[piece + 1] < mx) ++piece;
-                hp.last_piece[c] = mx ? piece : 0;
+                unsigned long long mx = (h_rng[2 * c + 1] + 1023ull) / 1024ull * 1024ull;     // max column + 1 (0: no entries)
+                if (mx > a->n_cols) mx = a->n_cols;
+                hp.x_bounds[c + 1] = mx > hp.x_bounds[c] ? mx : hp.x_bounds[c];
+                hp.last_piece[c] = c;
             }
-            // a chunk may start only when everything up to its last piece is in: make that monotone in c
-            for (int c = 1; c < chunks; ++c) if (hp.last_piece[c] < hp.last_piece[c - 1]) hp.last_piece[c] = hp.last_piece[c - 1];
+            hp.x_bounds[chunks] = a->n_cols;       // columns nobody reads are uploaded too: stage_x is a complete copy of x
             hp.ev_x.resize(chunks); hp.ev_y.resize(chunks);
             for (int c = 0; c < chunks; ++c) {
                 SMB_CUDA(cudaEventCreateWithFlags(&hp.ev_x[c], cudaEventDisableTiming));
