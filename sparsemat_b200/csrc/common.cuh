@@ -181,6 +181,12 @@ namespace smb {
 // the side stream (behind the halo receive) with their own partials buffer.
 struct LaunchRedirect { cudaStream_t stream = nullptr; double* partials = nullptr; };
 extern thread_local LaunchRedirect g_redirect;
+// SMs a persistent (ring) launch leaves free: dist.cu sets it for the interior product so that the NCCL send/recv kernel of
+// the halo exchange, queued on the side stream, finds an SM while the interior is still running.
+extern thread_local int g_ring_reserve_sms;
+// Upper bound on the CTAs of a persistent (ring) launch (0 = none): boundary-row launches that run beside the interior
+// kernel use as many CTAs as it left slots, each walking several blocks through its ring.
+extern thread_local int g_ring_grid_cap;
 // Set while an SpMV reads a caller-owned (smb200_vec_wrap) vector: such memory has no padding behind its last element,
 // so kernels must not round bulk copies of it up to 16 bytes.
 extern thread_local bool g_x_unpadded;

@@ -87,6 +87,12 @@ __global__ void pack_kernel(const T* __restrict__ x, const uint64_t* __restrict_
 
 }  // namespace smb
 
+// Default number of SMs a ring interior leaves free for the exchange: 0 = the halo is awaited first.  Measured on B200
+// (256^3 slab per GPU, profiles/dist_schedules_r01.log): at 2 GPUs leaving 8 SMs and overlapping ties with halo-first
+// (0.149 vs 0.150 ms), fewer SMs lose (the boundary rows crawl through the few free slots); at 4 GPUs halo-first wins
+// clearly (0.160 vs 0.195 ms).  SMB200_DIST_RESERVE_SMS / SMB200_DIST_OVERLAP keep the other schedules reachable.
+namespace smb { constexpr int kDistReserveSms = 0; }
+
 struct smb200_dist {
     smb200_ctx* ctx = nullptr;
     int vt = SMB200_F32, it = SMB200_U32;
@@ -170,10 +176,14 @@ static smb200_status dist_spmv_impl(smb200_dist* d, void* x, void* y, double* S)
     // stream and slip in between the interior's waves.  Persistent ring interior (it holds every SM until it is done, so a
     // concurrent kernel only perturbs it — measured 298 us vs 269 us on 2 GPUs): boundary rows follow on the main stream.
     static const int overlap_env = []{ const char* e = getenv("SMB200_DIST_OVERLAP"); return e ? (e[0] == '0' ? 0 : 1) : -1; }();
+    // SMs the persistent ring interior leaves to the NCCL send/recv kernel (set NCCL_MAX_P2P_NCHANNELS to the same number:
+    // one CTA per channel); 0 = the ring takes every SM and the halo is awaited first
+    static const int reserve_env = []{ const char* e = getenv("SMB200_DIST_RESERVE_SMS"); return e ? atoi(e) : kDistReserveSms; }();
     const bool overlap = overlap_env >= 0 ? overlap_env == 1 : d->plan_int.variant != SMB200_SPMV_RING;
-    if (exchange && !overlap && m->plan.built && m->plan.variant == SMB200_SPMV_RING) {
-        // Persistent ring: it owns every SM until it is done, and a NCCL send/recv kernel that arrives meanwhile finds no SM
-        // to run on (measured: the exchange then completes only after the interior, +60 us on ranks with two neighbours).
+    const bool ring_int = d->plan_int.variant == SMB200_SPMV_RING && d->int_end > d->int_begin;
+    if (exchange && !overlap && !(ring_int && reserve_env > 0) && m->plan.built && m->plan.variant == SMB200_SPMV_RING) {
+        // Persistent ring on every SM: a NCCL send/recv kernel that arrives meanwhile finds no SM to run on (measured: the
+        // exchange then completes only after the interior, +60 us on ranks with two neighbours).
         // So: halo first (~20 us over NVLink), then ONE launch over all local rows.
         SMB_CUDA(cudaEventRecord(ctx->ev_b, ctx->aux_stream));
         SMB_TRY(dist_exchange_end(d));
@@ -181,9 +191,15 @@ static smb200_status dist_spmv_impl(smb200_dist* d, void* x, void* y, double* S)
         return spmv_launch_plan(m, m->plan, 0, d->n_local, x, y, nullptr, 0);
     }
     if (exchange && !overlap) {
+        // Interior on the main stream while the exchange runs on the side stream (a ring interior leaves it a few SMs),
+        // then the boundary rows once the ghosts are in.
         SMB_CUDA(cudaEventRecord(ctx->ev_b, ctx->aux_stream));
-        if (S) SMB_TRY(spmv_launch_cg(m, d->plan_int, d->int_begin, d->int_end, x, y, x, S, 0, true));
-        else SMB_TRY(spmv_launch_plan(m, d->plan_int, d->int_begin, d->int_end, x, y, nullptr, 0));
+        g_ring_reserve_sms = ring_int ? reserve_env : 0;
+        smb200_status sti;
+        if (S) sti = spmv_launch_cg(m, d->plan_int, d->int_begin, d->int_end, x, y, x, S, 0, true);
+        else sti = spmv_launch_plan(m, d->plan_int, d->int_begin, d->int_end, x, y, nullptr, 0);
+        g_ring_reserve_sms = 0;
+        SMB_TRY(sti);
         SMB_TRY(dist_exchange_end(d));
         if (S) {
             SMB_TRY(spmv_launch_cg(m, d->plan_lo, 0, d->int_begin, x, y, x, S, 1, d->int_end == d->int_begin));
@@ -204,6 +220,8 @@ static smb200_status dist_spmv_impl(smb200_dist* d, void* x, void* y, double* S)
         }
         g_redirect.stream = ctx->aux_stream;
         g_redirect.partials = S ? ctx->red_partials_aux : nullptr;
+        // beside a ring interior the boundary launches only get the slots it leaves free: two CTAs per reserved SM
+        if (ring_int && reserve_env > 0) g_ring_grid_cap = 2 * reserve_env;
     }
     smb200_status st = SMB200_OK;
     if (S) {
@@ -216,10 +234,13 @@ static smb200_status dist_spmv_impl(smb200_dist* d, void* x, void* y, double* S)
         if (st == SMB200_OK) st = spmv_launch_plan(m, d->plan_hi, d->int_end, d->n_local, x, y, nullptr, 0);
     }
     g_redirect = LaunchRedirect();
+    g_ring_grid_cap = 0;
     SMB_TRY(st);
     if (exchange) SMB_CUDA(cudaEventRecord(ctx->ev_b, ctx->aux_stream));
+    g_ring_reserve_sms = (exchange && ring_int) ? reserve_env : 0;
     if (S) st = spmv_launch_cg(m, d->plan_int, d->int_begin, d->int_end, x, y, x, S, 0, true);
     else st = spmv_launch_plan(m, d->plan_int, d->int_begin, d->int_end, x, y, nullptr, 0);
+    g_ring_reserve_sms = 0;
     g_redirect = LaunchRedirect();
     SMB_TRY(st);
     SMB_TRY(dist_exchange_end(d));

@@ -1474,8 +1474,11 @@ static smb200_status launch_typed(smb200_crs* m, const SpmvPlan& p, uint64_t rb,
             SMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, kRingThreads, smem));
             if (resident < 1) resident = 1;
             if (resident > ctas) resident = ctas;
-            uint64_t grid = (uint64_t)ctx->sm_count * (uint64_t)resident;
+            int sms = ctx->sm_count - g_ring_reserve_sms;
+            if (sms < 1) sms = 1;
+            uint64_t grid = (uint64_t)sms * (uint64_t)resident;
             if (grid > p.n_blocks) grid = p.n_blocks;
+            if (g_ring_grid_cap > 0 && grid > (uint64_t)g_ring_grid_cap) grid = (uint64_t)g_ring_grid_cap;
             g_last_pipe_grid = (unsigned)grid;
             kern<<<(unsigned)grid, kRingThreads, smem, st>>>(vals, cols, offs, (const I*)p.blk_rows, (const I*)p.blk_nnz, p.seg_lo, p.seg_len,
                                                            (unsigned)p.n_blocks, sh.cap, p.ocap, xcap, colb, (unsigned)stages, xwin_ok,
