@@ -155,6 +155,15 @@ def cpu_reference(steps: int, warmup: int, want_cg: bool):
         "serial_sample": f"{len(serial)} SpMVs of the restated SparseMatCRS mvp on 1 core (what the reference executes)",
         "gflops": 2 * vals.size / np.mean(par) / 1e9, "serial_gflops": 2 * vals.size / np.mean(serial) / 1e9,
     }
+    # the sparsemat_par path as shipped: SparseMatPar<SparseMatIndexList>, serial default mvp through the block dispatch
+    # (sparsemat_par.rs:71-140) — bounded sample: the 128^3 operator in 16 row blocks, assembled through the restated API
+    pn = 128
+    _, psec, pasm = orc.par_laplace_mvp(np.float32, np.uint32, 16, pn, pn, pn, orc.uniform(np.float32, 2, pn ** 3), reps=3)
+    pB = algorithmic_bytes(pn ** 3, pn ** 3, laplace_nnz(pn, pn, pn), 4, 4)
+    out.update({"par_serial_value": pB / psec / 1e9, "par_serial_cores": 1, "par_assemble_s": pasm,
+                "par_serial_sample": "3 products of the 128^3 f32/u32 Laplacian held as SparseMatPar<SparseMatIndexList> in 16 row "
+                                     "blocks, serial default mvp through the block dispatch (what sparsemat_par.rs executes today); "
+                                     "best of 3"})
     if want_cg:
         v64 = vals.astype(np.float64)
         b = orc.mvp(v64, cols, offs, orc.uniform(np.float64, 6, n))

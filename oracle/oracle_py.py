@@ -242,6 +242,20 @@ def to_crs_raw(n_rows, columns, values, pos_start, nxt):
     return ov, oc, oo
 
 
+def par_laplace_mvp(vdt, idt, n_blocks, nx, ny, nz, x, reps=1):
+    """The sparsemat_par path as shipped (sparsemat_par.rs:71-140): the Laplacian assembled through SparseMatPar::set into
+    IndexList blocks, then the SERIAL default mvp through the block dispatch.  Returns (y, seconds per product, seconds of
+    assembly)."""
+    n = nx * ny * nz
+    x = np.ascontiguousarray(x, dtype=vdt)
+    assert x.size >= n
+    y = np.empty(n, vdt)
+    sec, asm = C.c_double(), C.c_double()
+    _chk(fn("orc_par_laplace_mvp", suffix(vdt, idt))(_u64(n_blocks), _u64(nx), _u64(ny), _u64(nz), _p(x), _p(y), C.c_uint(reps),
+                                                   C.byref(sec), C.byref(asm)))
+    return y, sec.value, asm.value
+
+
 def par_locate(n_blocks, max_rows, row):
     out = np.zeros(2, np.uint64)
     _chk(lib().orc_par_locate(_u64(n_blocks), _u64(max_rows), _u64(row), _p(out)))

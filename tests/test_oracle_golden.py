@@ -97,6 +97,20 @@ def test_threaded_mvp_equals_serial_bit_for_bit(orc):
     assert np.array_equal(orc.mvp(vals, cols, offs, x, threads=4), orc.mvp(vals, cols, offs, x))
 
 
+def test_par_path_as_shipped_equals_crs_mvp_bit_for_bit(orc):
+    """SparseMatPar<SparseMatIndexList> assembled through set() + the serial default mvp through the block dispatch
+    (sparsemat_par.rs:71-140, sparsematrix.rs:146-158) sums every row in insertion order: the same bits as to_crs + mvp."""
+    for vdt, idt in [(np.float32, np.uint32), (np.float64, np.uint64)]:
+        for nx, ny, nz, nb in [(20, 12, 9, 4), (33, 17, 1, 3), (5, 1, 1, 5), (16, 16, 16, 16)]:
+            n = nx * ny * nz
+            x = orc.uniform(vdt, 7, n)
+            y, sec, asm = orc.par_laplace_mvp(vdt, idt, nb, nx, ny, nz, x)
+            v, c, o = orc.laplace(vdt, idt, nx, ny, nz)
+            assert np.array_equal(y, orc.mvp(v, c, o, x)) and sec > 0 and asm > 0
+    with pytest.raises(orc.OraclePanic):                                   # R = max_n_rows / n_blocks == 0 (sparsemat_par.rs:21,32)
+        orc.par_laplace_mvp(np.float32, np.uint32, 8, 2, 2, 1, orc.uniform(np.float32, 7, 4))
+
+
 def test_committed_fixtures(orc):
     """Oracle outputs for seeded inputs, committed: guards the oracle itself against drift."""
     fx = np.load(os.path.join(HERE, "golden", "oracle_fixtures.npz"))
