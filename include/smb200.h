@@ -102,7 +102,9 @@ typedef struct {
     uint64_t n_xwin_blocks;   /* RING: row blocks whose x segments are staged by TMA (the rest gather from global) */
     uint64_t nnz_c16;         /* RING: non-zeros whose column is streamed as a 16-bit window position (plan-time index
                                * compression; the CRS arrays themselves are untouched)                                */
-    uint64_t stream_bytes;    /* bytes the planned kernel moves per product: algorithmic_bytes - nnz_c16*(sizeof I - 2)  */
+    uint64_t stream_bytes;    /* bytes the planned kernel moves per product:
+                               * algorithmic_bytes - (nnz_c16 + rows_o16)*(sizeof I - 2)                              */
+    uint64_t rows_o16;        /* RING: rows whose offsets are streamed as 16-bit block-relative numbers               */
 } smb200_plan_info;
 
 typedef struct {

@@ -22,7 +22,8 @@ def time_spmv(ctx, a, x, y, reps):
     return e0.elapsed_ms(e1) / reps
 
 
-ARMS = [("packed fill=60", {"SMB200_RING_FILL": "60"}), ("packed fill=70", {}), ("packed fill=80", {"SMB200_RING_FILL": "80"}),
+ARMS = [("packed fill=70 (default)", {}), ("packed fill=80", {"SMB200_RING_FILL": "80"}),
+        ("packed, full-width offsets", {"SMB200_RING_O16": "0"}),
         ("c16, worst-case stage", {"SMB200_RING_PACK": "0"}), ("full-width columns", {"SMB200_RING_C16": "0"})]
 
 
@@ -32,7 +33,7 @@ def ab(ctx, name, a, reps=200, caps=None):
     y = smb.DenseVec(ctx, a.n_rows(), a.dtype)
     ref = None
     for label, env in ARMS:
-        for k in ("SMB200_RING_FILL", "SMB200_RING_PACK", "SMB200_RING_C16"):
+        for k in ("SMB200_RING_FILL", "SMB200_RING_PACK", "SMB200_RING_C16", "SMB200_RING_O16"):
             os.environ.pop(k, None)
         os.environ.update(env)
         a.configure(smb.SPMV_RING)
@@ -43,9 +44,9 @@ def ab(ctx, name, a, reps=200, caps=None):
             ref = got
         same = bool(np.array_equal(got, ref))
         B, S = pi["algorithmic_bytes"], pi["stream_bytes"]
-        print(f"{name:8s} {label:22s} blocks={pi['n_blocks']:6d} nnz_c16={pi['nnz_c16']:>10d} "
+        print(f"{name:8s} {label:26s} blocks={pi['n_blocks']:6d} nnz_c16={pi['nnz_c16']:>10d} "
               f"{ms * 1e3:8.1f} us  effective {B / ms / 1e6:7.1f} GB/s  streamed {S / ms / 1e6:7.1f} GB/s  identical={same}", flush=True)
-    for k in ("SMB200_RING_FILL", "SMB200_RING_PACK", "SMB200_RING_C16"):
+    for k in ("SMB200_RING_FILL", "SMB200_RING_PACK", "SMB200_RING_C16", "SMB200_RING_O16"):
         os.environ.pop(k, None)
 
 

@@ -117,6 +117,9 @@ struct SpmvPlan {
     unsigned long long* seg_lo = nullptr; // RING: [4 * n_blocks] first column of each x segment of the block (aligned down)
     unsigned* seg_len = nullptr;        // RING: [4 * n_blocks] segment lengths in elements (0 = unused; all 0 = no window)
     unsigned ocap = 0, xcap = 0;        // RING: row-offset / x-window capacity of a stage (elements)
+    uint16_t* loffs = nullptr;          // RING, packed plans: 16-bit row offsets relative to each block's slice start
+    uint64_t loffs_row_begin = 0;       //       first row of the plan's range (the kernel derives a block's position from it)
+    uint64_t n_o16 = 0;                 //       rows whose offsets the kernel reads from loffs
     unsigned colb = 0;                  // RING: bytes per element of a stage's column area (2 = packed: every block compressed)
     uint64_t n_xwin = 0;                // RING: blocks whose columns fit <= 4 windows
     uint16_t* lcols = nullptr;          // RING: 16-bit window-relative columns of the windowed blocks (index compression);

@@ -704,6 +704,7 @@ struct RingDesc {
     long long delta[kNSeg];                  // window element index = column + delta
     unsigned xwin;                           // number of windows that cover the block; 0: gather x from global memory
     unsigned c16;                            // 1: the column area of the stage holds 16-bit indices into the staged windows
+    unsigned o16;                            // 1: the offset area holds 16-bit row offsets relative to a0, entry 0 = row r0
 };
 
 template <class T, class I, int NSEG> struct RingWin {
@@ -719,7 +720,20 @@ template <class T, class I, int NSEG> struct RingWin {
 };
 
 // Rows [r0, r1) of one staged block, one thread per row, starting at thread `lane_id` of `n_lanes` consumer threads.
-template <class T, class I, bool DOT, int NSEG>
+// The stage's row offsets: full width (absolute, entry 0 = row r0a) or 16 bits (relative to a0, entry 0 = row r0).
+template <class I, bool O16>
+__device__ __forceinline__ void ring_row_span(const I* so, uint64_t r, uint64_t r0, uint64_t r0a, uint64_t a0, unsigned& ka, unsigned& ke) {
+    if constexpr (O16) {
+        const uint16_t* so16 = reinterpret_cast<const uint16_t*>(so);
+        ka = so16[r - r0];
+        ke = so16[r - r0 + 1];
+    } else {
+        ka = (unsigned)((uint64_t)so[r - r0a] - a0);
+        ke = (unsigned)((uint64_t)so[r + 1 - r0a] - a0);
+    }
+}
+
+template <class T, class I, bool DOT, int NSEG, bool O16 = false>
 __device__ __forceinline__ double ring_rows(const T* sv, const I* sc, const I* so, const T* sx, const RingDesc& d,
                                             unsigned lane_id, unsigned n_lanes, const T* __restrict__ x, T* __restrict__ y,
                                             const T* __restrict__ w) {
@@ -729,7 +743,8 @@ __device__ __forceinline__ double ring_rows(const T* sv, const I* sc, const I* s
     win.d0 = (unsigned)d.delta[0]; win.d1 = (unsigned)d.delta[1]; win.d2 = (unsigned)d.delta[2]; win.d3 = (unsigned)d.delta[3];
     double acc = 0.0;
     for (uint64_t r = r0 + lane_id; r < r1; r += n_lanes) {
-        const unsigned ka = (unsigned)((uint64_t)so[r - r0a] - a0), ke = (unsigned)((uint64_t)so[r + 1 - r0a] - a0);
+        unsigned ka, ke;
+        ring_row_span<I, O16>(so, r, r0, r0a, a0, ka, ke);
         T wv = T(0);
         if constexpr (DOT) wv = __ldg(w + r);          // one coalesced load per row, in flight during the row's sum
         T sum = T(0);
@@ -750,13 +765,14 @@ __device__ __forceinline__ double ring_rows(const T* sv, const I* sc, const I* s
 // Same with compressed columns: the plan stored, for every non-zero of a windowed block, the 16-bit position of its
 // column inside the block's concatenated x windows, so a stage carries 2 bytes per column instead of sizeof(I) and the
 // consumer needs no window search.  The arithmetic (operands, order, roundings) is unchanged.
-template <class T, class I, bool DOT>
+template <class T, class I, bool DOT, bool O16>
 __device__ __forceinline__ double ring_rows_c16(const T* sv, const uint16_t* sc, const I* so, const T* sx, const RingDesc& d,
                                                 unsigned lane_id, unsigned n_lanes, T* __restrict__ y, const T* __restrict__ w) {
     const uint64_t r0 = d.r0, r1 = d.r1, a0 = d.a0, r0a = d.r0a;
     double acc = 0.0;
     for (uint64_t r = r0 + lane_id; r < r1; r += n_lanes) {
-        const unsigned ka = (unsigned)((uint64_t)so[r - r0a] - a0), ke = (unsigned)((uint64_t)so[r + 1 - r0a] - a0);
+        unsigned ka, ke;
+        ring_row_span<I, O16>(so, r, r0, r0a, a0, ka, ke);
         T wv = T(0);
         if constexpr (DOT) wv = __ldg(w + r);
         T sum = T(0);
@@ -774,7 +790,8 @@ spmv_ring_kernel(const T* __restrict__ vals, const I* __restrict__ cols, const I
                  const I* __restrict__ blk_rows, const I* __restrict__ blk_nnz, const unsigned long long* __restrict__ seg_lo,
                  const unsigned* __restrict__ seg_len, unsigned n_blocks, unsigned cap, unsigned ocap, unsigned xcap,
                  unsigned colb, unsigned stages, int xwin_ok, const uint16_t* __restrict__ lcols, unsigned long long lcols_base,
-                 const T* __restrict__ x, T* __restrict__ y, DotArgs dot) {
+                 const uint16_t* __restrict__ loffs, unsigned long long row_begin, const T* __restrict__ x, T* __restrict__ y,
+                 DotArgs dot) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full[kPipeMaxStages];    // producer -> consumers: the stage's bytes have landed
     __shared__ __align__(8) uint64_t empty[kPipeMaxStages];   // consumers -> producer: every consumer warp has left the stage
@@ -784,7 +801,7 @@ spmv_ring_kernel(const T* __restrict__ vals, const I* __restrict__ cols, const I
     const unsigned tid = threadIdx.x;
     const size_t o_cols = (size_t)cap * sizeof(T);
     const size_t o_offs = o_cols + (size_t)cap * colb;          // colb = 2: every block of the plan streams 16-bit columns
-    const size_t o_x = o_offs + (size_t)(ocap + 8) * sizeof(I);
+    const size_t o_x = o_offs + (size_t)(ocap + 8) * (loffs ? 2 : sizeof(I));   // loffs: ocap is a multiple of 8
     const size_t stage_bytes = o_x + (size_t)xcap * sizeof(T);
     double stop = 0.0;
     if constexpr (DOT) { if (dot.done != nullptr) stop = __ldcg(dot.done); }
@@ -813,8 +830,12 @@ spmv_ring_kernel(const T* __restrict__ vals, const I* __restrict__ cols, const I
                 // slices start at a multiple of 8 elements: 16-byte aligned for 2-byte compressed columns as well
                 const unsigned long long a0 = n0 & ~7ull, r0a = r0 & ~(unsigned long long)(OA - 1);
                 const unsigned count = (unsigned)(((n1 - a0) + 7ull) & ~7ull);
-                const unsigned ocount = (unsigned)(((r1 + 1 - r0a) + (OA - 1)) & ~(unsigned long long)(OA - 1));
-                d.r0 = r0; d.r1 = r1; d.a0 = a0; d.r0a = r0a;
+                // row offsets: full width from the CRS array, or the plan's 16-bit copy (block b's entries start at a multiple of 8)
+                const bool o16 = loffs != nullptr;
+                const unsigned ocount = o16 ? (unsigned)(((r1 - r0 + 1) + 7ull) & ~7ull)
+                                            : (unsigned)(((r1 + 1 - r0a) + (OA - 1)) & ~(unsigned long long)(OA - 1));
+                const unsigned obytes = ocount * (o16 ? 2u : (unsigned)sizeof(I));
+                d.r0 = r0; d.r1 = r1; d.a0 = a0; d.r0a = r0a; d.o16 = o16 ? 1u : 0u;
                 unsigned xtotal = 0, nseg = 0;
 #pragma unroll
                 for (int i = 0; i < kNSeg; ++i) {
@@ -828,7 +849,7 @@ spmv_ring_kernel(const T* __restrict__ vals, const I* __restrict__ cols, const I
                 d.xwin = xw ? nseg : 0u;
                 d.c16 = c16 ? 1u : 0u;
                 const unsigned cbytes = count * (c16 ? 2u : (unsigned)sizeof(I));
-                unsigned bytes = count * (unsigned)sizeof(T) + cbytes + ocount * (unsigned)sizeof(I);
+                unsigned bytes = count * (unsigned)sizeof(T) + cbytes + obytes;
                 if (xw) bytes += xtotal * (unsigned)sizeof(T);
                 mbar_expect_tx(&full[s], bytes);
                 if (count) {
@@ -836,7 +857,8 @@ spmv_ring_kernel(const T* __restrict__ vals, const I* __restrict__ cols, const I
                     if (c16) bulk_g2s(base + o_cols, lcols + (a0 - lcols_base), cbytes, &full[s]);
                     else bulk_g2s(base + o_cols, cols + a0, cbytes, &full[s]);
                 }
-                bulk_g2s(base + o_offs, offs + r0a, ocount * (unsigned)sizeof(I), &full[s]);
+                if (o16) bulk_g2s(base + o_offs, loffs + (((r0 - row_begin) + 8ull * b) & ~7ull), obytes, &full[s]);
+                else bulk_g2s(base + o_offs, offs + r0a, obytes, &full[s]);
                 if (xw) {
                     unsigned at = 0;
 #pragma unroll
@@ -859,9 +881,15 @@ spmv_ring_kernel(const T* __restrict__ vals, const I* __restrict__ cols, const I
             const I* so = reinterpret_cast<const I*>(base + o_offs);
             const T* sx = reinterpret_cast<const T*>(base + o_x);
             const T* w = (const T*)dot.w;
-            if (d.c16) acc += ring_rows_c16<T, I, DOT>(sv, reinterpret_cast<const uint16_t*>(base + o_cols), so, sx, d, lane_id, n_lanes, y, w);
-            else switch (d.xwin) {                // number of x windows of the block (block-uniform)
-                case 0: acc += ring_rows<T, I, DOT, 0>(sv, sc, so, sx, d, lane_id, n_lanes, x, y, w); break;
+            if (d.c16) {
+                const uint16_t* sc16 = reinterpret_cast<const uint16_t*>(base + o_cols);
+                if (d.o16) acc += ring_rows_c16<T, I, DOT, true>(sv, sc16, so, sx, d, lane_id, n_lanes, y, w);
+                else acc += ring_rows_c16<T, I, DOT, false>(sv, sc16, so, sx, d, lane_id, n_lanes, y, w);
+            } else switch (d.xwin) {              // number of x windows of the block (block-uniform)
+                case 0:
+                    if (d.o16) acc += ring_rows<T, I, DOT, 0, true>(sv, sc, so, sx, d, lane_id, n_lanes, x, y, w);
+                    else acc += ring_rows<T, I, DOT, 0, false>(sv, sc, so, sx, d, lane_id, n_lanes, x, y, w);
+                    break;
                 case 1: acc += ring_rows<T, I, DOT, 1>(sv, sc, so, sx, d, lane_id, n_lanes, x, y, w); break;
                 case 2: acc += ring_rows<T, I, DOT, 2>(sv, sc, so, sx, d, lane_id, n_lanes, x, y, w); break;
                 case 3: acc += ring_rows<T, I, DOT, 3>(sv, sc, so, sx, d, lane_id, n_lanes, x, y, w); break;
@@ -981,6 +1009,20 @@ ring_compress_kernel(const I* __restrict__ cols, const I* __restrict__ blk_nnz, 
     if (threadIdx.x == 0) atomicAdd(n_c16, (unsigned long long)(n1 - n0));
 }
 
+// Plan time, one CTA per block: 16-bit row offsets relative to the start of the block's slice (a0 = blk_nnz[b] & ~7).
+// Block b's rows + 1 entries start at ((r0 - row_begin) + 8 b) & ~7, a multiple of 8 entries (16 bytes) that never
+// reaches into the previous block's entries.
+template <class I>
+__global__ void __launch_bounds__(128)
+ring_offsets16_kernel(const I* __restrict__ offs, const I* __restrict__ blk_rows, const I* __restrict__ blk_nnz,
+                      unsigned long long row_begin, uint16_t* __restrict__ loffs) {
+    const unsigned long long b = blockIdx.x;
+    const unsigned long long r0 = (unsigned long long)blk_rows[b], r1 = (unsigned long long)blk_rows[b + 1];
+    const unsigned long long a0 = (unsigned long long)blk_nnz[b] & ~7ull;
+    const unsigned long long base = ((r0 - row_begin) + 8ull * b) & ~7ull;
+    for (unsigned long long i = threadIdx.x; i <= r1 - r0; i += 128) loffs[base + i] = (uint16_t)((unsigned long long)offs[r0 + i] - a0);
+}
+
 // ---- plan construction --------------------------------------------------------------------------------
 // Split points of the merge coordinate key(r) = (r - rb) + (offs[r] - offs[rb]) at multiples of `target`.
 template <class I>
@@ -1087,6 +1129,7 @@ void plan_free(SpmvPlan& p) {
     if (p.seg_lo) cudaFree(p.seg_lo);
     if (p.seg_len) cudaFree(p.seg_len);
     if (p.lcols) cudaFree(p.lcols);
+    if (p.loffs) cudaFree(p.loffs);
     if (p.blk_win) cudaFree(p.blk_win);
     p = SpmvPlan();
 }
@@ -1252,6 +1295,7 @@ static smb200_status ring_plan(smb200_crs* m, SpmvPlan& p, uint64_t rb, uint64_t
     const size_t ts = vsize(m->vt), is = isize(m->it);
     const uint64_t rows = re - rb, nnz = oe - ob;
     const bool want_c16 = env_int("SMB200_RING_C16", 1) != 0;
+    const bool want_o16 = env_int("SMB200_RING_O16", 1) != 0;
     bool packed = false;
     if (want_c16 && nnz > 0 && env_int("SMB200_RING_PACK", 1) != 0 && getenv("SMB200_RING_CAP") == nullptr) {
         const double mean = (double)nnz / (double)rows;
@@ -1273,8 +1317,8 @@ static smb200_status ring_plan(smb200_crs* m, SpmvPlan& p, uint64_t rb, uint64_t
             cudaError_t e = cudaMemcpyAsync(h_ext, d_ext, sizeof h_ext, cudaMemcpyDeviceToHost, ctx->stream);
             if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
             if (e != cudaSuccess) { cudaFree(d_ext); SMB_CUDA(e); }
-            const size_t cap = (size_t)((h_ext[0] + 7ull) & ~7ull), ocap = (size_t)((h_ext[1] + 3ull) & ~3ull);
-            const size_t fixed = cap * (ts + 2) + (ocap + 8) * is;
+            const size_t cap = (size_t)((h_ext[0] + 7ull) & ~7ull), ocap = (size_t)((h_ext[1] + 7ull) & ~7ull);
+            const size_t fixed = cap * (ts + 2) + (ocap + 8) * (want_o16 && cap + 16 < 65536 ? 2 : is);
             if (fixed + 64 * ts > kRingStageBudget) continue;
             size_t xc = (kRingStageBudget - fixed) / ts;
             if (xc > 65536) xc = 65536;
@@ -1318,6 +1362,18 @@ static smb200_status ring_plan(smb200_crs* m, SpmvPlan& p, uint64_t rb, uint64_t
         cudaFree(d_n);
         SMB_CUDA(e2);
         p.n_c16 = h_n;
+    }
+    // packed plans also stream 16-bit row offsets (relative to the block's slice): another sizeof(I) - 2 bytes per row
+    if (packed && want_o16 && p.lcols && (size_t)p.cap + 16 < 65536) {
+        const size_t n_o = (size_t)rows + 8 * (size_t)p.n_blocks + 16;
+        SMB_CUDA(cudaMalloc(&p.loffs, n_o * sizeof(uint16_t) + kPadBytes));
+        cudaMemsetAsync(p.loffs, 0, n_o * sizeof(uint16_t) + kPadBytes, ctx->stream);
+        if (m->it == SMB200_U64) ring_offsets16_kernel<uint64_t><<<(unsigned)p.n_blocks, 128, 0, ctx->stream>>>((const uint64_t*)m->offsets, (const uint64_t*)p.blk_rows, (const uint64_t*)p.blk_nnz, rb, p.loffs);
+        else ring_offsets16_kernel<uint32_t><<<(unsigned)p.n_blocks, 128, 0, ctx->stream>>>((const uint32_t*)m->offsets, (const uint32_t*)p.blk_rows, (const uint32_t*)p.blk_nnz, rb, p.loffs);
+        count_launch();
+        SMB_CUDA(cudaGetLastError());
+        p.loffs_row_begin = rb;
+        p.n_o16 = rows;
     }
     return SMB200_OK;
 }
@@ -1455,7 +1511,7 @@ static smb200_status launch_typed(smb200_crs* m, const SpmvPlan& p, uint64_t rb,
             // without windows (borrowed, unpadded x) every block stages its full-width columns and no x
             const unsigned colb = (xwin_ok && p.colb == 2) ? 2u : (unsigned)sizeof(I);
             const unsigned xcap = xwin_ok ? p.xcap : 0u;
-            const size_t stage = (size_t)sh.cap * (sizeof(T) + colb) + (size_t)(p.ocap + 8) * sizeof(I) + (size_t)xcap * sizeof(T);
+            const size_t stage = (size_t)sh.cap * (sizeof(T) + colb) + (size_t)(p.ocap + 8) * (p.loffs ? 2 : sizeof(I)) + (size_t)xcap * sizeof(T);
             // two CTAs per SM, two stages each: one block is consumed while the next one lands, and the second CTA's
             // consumers fill the issue slots the first one leaves idle
             int ctas = env_int("SMB200_RING_CTAS", 2);
@@ -1482,7 +1538,8 @@ static smb200_status launch_typed(smb200_crs* m, const SpmvPlan& p, uint64_t rb,
             g_last_pipe_grid = (unsigned)grid;
             kern<<<(unsigned)grid, kRingThreads, smem, st>>>(vals, cols, offs, (const I*)p.blk_rows, (const I*)p.blk_nnz, p.seg_lo, p.seg_len,
                                                            (unsigned)p.n_blocks, sh.cap, p.ocap, xcap, colb, (unsigned)stages, xwin_ok,
-                                                           xwin_ok ? p.lcols : nullptr, (unsigned long long)p.lcols_base, xx, yy, dot);
+                                                           xwin_ok ? p.lcols : nullptr, (unsigned long long)p.lcols_base, p.loffs,
+                                                           (unsigned long long)p.loffs_row_begin, xx, yy, dot);
         } else if (p.variant == SMB200_SPMV_STREAM_PIPE) {
             int stages = env_int("SMB200_PIPE_STAGES", 3);
             if (stages < 3) stages = 3;     // the kernel reads the descriptor of block i + 1 during iteration i
@@ -1656,7 +1713,8 @@ smb200_status smb200_crs_plan_info(const smb200_crs* cm, smb200_plan_info* out) 
     out->launches_per_spmv = 1;
     out->n_xwin_blocks = m->plan.n_xwin;
     out->nnz_c16 = m->plan.n_c16;
-    out->stream_bytes = out->algorithmic_bytes - m->plan.n_c16 * (isize(m->it) - 2);
+    out->rows_o16 = m->plan.n_o16;
+    out->stream_bytes = out->algorithmic_bytes - (m->plan.n_c16 + m->plan.n_o16) * (isize(m->it) - 2);
     return SMB200_OK;
 }
 
@@ -1698,24 +1756,38 @@ smb200_status smb200_spmv_host(smb200_crs* a, const void* x_host, uint64_t nx, v
     // ---- pipelined path: H2D pieces of x | row chunks | D2H slices of y on three streams ---------------------------
     HostPipe& hp = a->hp;
     if (!hp.built) {
+        // ~8 MiB of y per chunk (measured best on C2: every chunk costs ~14 us of launches, events and copy set-up).  The
+        // upload of the first piece is the head of the pipeline (nothing else can run yet) and the download of the last slice
+        // its tail, so the chunks at both ends are smaller: taper 1 = half size, taper 2 = 1/8, 1/4, 1/2 of a full chunk.
         int chunks = env_int("SMB200_HOST_CHUNKS", 0);
-        // ~8 MiB of y per chunk (measured best on C2: every chunk costs ~14 us of launches, events and copy set-up); the
-        // first and the last chunk are half as large: the upload of the first piece is the head of the pipeline (nothing
-        // else can run yet) and the download of the last slice its tail
-        if (chunks <= 0) { chunks = (int)((yb + (8u << 20) - 1) / (8u << 20)); if (chunks >= 4) ++chunks; }
-        if (chunks > 64) chunks = 64;
+        if (chunks <= 0) chunks = (int)((yb + (8u << 20) - 1) / (8u << 20));
+        if (chunks > 56) chunks = 56;
         if (chunks < 1 || env_int("SMB200_HOST_PIPE", 1) == 0) chunks = 1;
+        const int taper = chunks >= 4 ? env_int("SMB200_HOST_TAPER", 1) : 0;
+        std::vector<double> weights;
+        if (taper == 2) {
+            weights = {0.125, 0.25, 0.5};
+            weights.insert(weights.end(), (size_t)chunks - 2, 1.0);
+            weights.insert(weights.end(), {0.5, 0.25, 0.125});
+        } else if (taper == 1) {
+            weights.assign((size_t)chunks + 1, 1.0);
+            weights.front() = weights.back() = 0.5;
+        } else {
+            weights.assign((size_t)chunks, 1.0);
+        }
+        chunks = (int)weights.size();
+        double total_w = 0.0;
+        for (double w : weights) total_w += w;
         hp.n_chunks = chunks;
         hp.row_bounds.assign(chunks + 1, a->n_rows);
         hp.x_bounds.assign(chunks + 1, a->n_cols);
-        const bool taper = chunks >= 4 && env_int("SMB200_HOST_TAPER", 1) != 0;
-        const uint64_t units = taper ? 2 * (uint64_t)chunks - 2 : (uint64_t)chunks;     // weights 1,2,2,...,2,1
+        double at = 0.0;
         for (int c = 0; c < chunks; ++c) {
-            const uint64_t at = taper ? (c == 0 ? 0 : 2 * (uint64_t)c - 1) : (uint64_t)c;
-            hp.row_bounds[c] = ((a->n_rows * at / units) + 1023) / 1024 * 1024;
-            hp.x_bounds[c] = ((a->n_cols * at / units) + 1023) / 1024 * 1024;
+            hp.row_bounds[c] = ((uint64_t)((double)a->n_rows * (at / total_w)) + 1023) / 1024 * 1024;
+            hp.x_bounds[c] = ((uint64_t)((double)a->n_cols * (at / total_w)) + 1023) / 1024 * 1024;
             if (hp.row_bounds[c] > a->n_rows) hp.row_bounds[c] = a->n_rows;
             if (hp.x_bounds[c] > a->n_cols) hp.x_bounds[c] = a->n_cols;
+            at += weights[c];
         }
         hp.row_bounds[0] = 0; hp.x_bounds[0] = 0;
         hp.last_piece.assign(chunks, chunks - 1);

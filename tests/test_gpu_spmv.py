@@ -130,8 +130,9 @@ def test_ring_kernel_windows_and_fallbacks(smb, orc, ctx, vdt, idt):
         info = a.plan_info()
         assert info["variant"] == smb.SPMV_RING and info["n_xwin_blocks"] == info["n_blocks"]   # every block got its windows
         # ... and with them 16-bit window positions instead of its columns (plan-time index compression)
-        assert info["nnz_c16"] == vals.size
-        assert info["stream_bytes"] == info["algorithmic_bytes"] - vals.size * (np.dtype(idt).itemsize - 2)
+        # and, the plan being packed, 16-bit block-relative row offsets as well
+        assert info["nnz_c16"] == vals.size and info["rows_o16"] == n
+        assert info["stream_bytes"] == info["algorithmic_bytes"] - (vals.size + n) * (np.dtype(idt).itemsize - 2)
         x = orc.uniform(vdt, 21, n)
         want = orc.mvp(vals, cols, offs, x)
         xd = smb.DenseVec.from_vec(ctx, x)
@@ -147,7 +148,8 @@ def test_ring_kernel_windows_and_fallbacks(smb, orc, ctx, vdt, idt):
     case = cases.ragged(41, 6000, 900_000, 9, vdt, idt)                        # scattered columns: no windows
     a = smb.SparseMatCRS.from_raw_parts(ctx, *case).configure(smb.SPMV_RING)
     assert a.plan_info()["variant"] == smb.SPMV_RING and a.plan_info()["n_xwin_blocks"] == 0
-    assert a.plan_info()["nnz_c16"] == 0 and a.plan_info()["stream_bytes"] == a.plan_info()["algorithmic_bytes"]
+    assert a.plan_info()["nnz_c16"] == 0 and a.plan_info()["rows_o16"] == 0
+    assert a.plan_info()["stream_bytes"] == a.plan_info()["algorithmic_bytes"]
     x = np.random.default_rng(1).uniform(-1, 1, case[1]).astype(vdt)
     assert np.array_equal(a.mvp(smb.DenseVec.from_vec(ctx, x)).to_numpy(), orc.mvp(case[2], case[3], case[4], x))
     long_rows = cases.ragged(42, 300, 5000, 90, vdt, idt)                      # rows > 32 entries: not RING's business
@@ -205,6 +207,10 @@ def test_ring_windows_on_random_multi_diagonal_matrices(smb, orc, ctx, seed):
     assert 0 <= info["nnz_c16"] <= vals.size and (info["nnz_c16"] > 0) == (info["n_xwin_blocks"] > 0)
     import os
     try:
+        os.environ["SMB200_RING_O16"] = "0"                                # packed (if every block has windows), full-width offsets
+        a.configure(smb.SPMV_RING)
+        assert a.plan_info()["rows_o16"] == 0
+        assert np.array_equal(a.mvp(smb.DenseVec.from_vec(ctx, x)).to_numpy(), want), (seed, "o16 off", a.plan_info())
         os.environ["SMB200_RING_PACK"] = "0"                               # worst-case stage capacities, mixed blocks
         a.configure(smb.SPMV_RING)
         assert np.array_equal(a.mvp(smb.DenseVec.from_vec(ctx, x)).to_numpy(), want), (seed, "unpacked", a.plan_info())
@@ -215,6 +221,7 @@ def test_ring_windows_on_random_multi_diagonal_matrices(smb, orc, ctx, seed):
     finally:
         os.environ.pop("SMB200_RING_C16", None)
         os.environ.pop("SMB200_RING_PACK", None)
+        os.environ.pop("SMB200_RING_O16", None)
 
 
 def test_sparsemat_par_known_answer_and_blocked_product(smb, orc, ctx):
