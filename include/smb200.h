@@ -42,7 +42,8 @@ enum {
     SMB200_ERR_SIZE_MISMATCH = 5, /* linearsolver.rs:33-36 "Matrix and vector size mismatch"          */
     SMB200_ERR_NCCL = 6,
     SMB200_ERR_UNSUPPORTED = 7,
-    SMB200_ERR_OOM = 8
+    SMB200_ERR_OOM = 8,
+    SMB200_ERR_IO = 9             /* smb200_crsfile_* / crs_save / crs_load: open/read/write failure, bad or damaged file */
 };
 
 typedef enum { SMB200_F32 = 0, SMB200_F64 = 1 } smb200_vtype;   /* types.rs:70-77 */
@@ -191,6 +192,19 @@ smb200_status smb200_crs_from_indexlist(smb200_ctx* ctx, smb200_vtype vt, smb200
                                         uint64_t n_cols, uint64_t nnz, const void* columns, const void* values,
                                         const void* pos_start, const void* index_list, smb200_crs** out);
 smb200_status smb200_crs_free(smb200_crs* m);
+/* Binary CRS container (additive; the reference only writes text/PBM, sparsematrix.rs:304-338, and reads nothing):
+ * a 56-byte header (magic "SMBCRS01", value/index type, n_rows, n_cols, nnz, FNV-1a 64 of the payload) followed by
+ * offset_rows[n_rows+1], columns[nnz], values[nnz] exactly as SparseMatCRS holds them (sparsemat_crs.rs:9-17), each
+ * zero-padded to 8 bytes; little endian.  ERR_IO on open/read/write failures, foreign or truncated files and checksum
+ * mismatches.  crsfile_* are host-only (no device needed): info fills vt, it and out3 = {n_rows, n_cols, nnz} so the
+ * caller can size the buffers for crsfile_read.  crs_save downloads and writes; crs_load reads and uploads (with the
+ * validation of smb200_crs_upload). */
+smb200_status smb200_crsfile_write(const char* path, smb200_vtype vt, smb200_itype it, uint64_t n_rows, uint64_t n_cols,
+                                   uint64_t nnz, const void* values, const void* columns, const void* offset_rows);
+smb200_status smb200_crsfile_info(const char* path, int32_t* vt, int32_t* it, uint64_t* out3);
+smb200_status smb200_crsfile_read(const char* path, void* values, void* columns, void* offset_rows);
+smb200_status smb200_crs_save(const smb200_crs* m, const char* path);
+smb200_status smb200_crs_load(smb200_ctx* ctx, const char* path, smb200_crs** out);
 /* out3 = {n_rows, n_cols, n_non_zero_entries} (sparsemat_crs.rs:124-134). */
 smb200_status smb200_crs_dims(const smb200_crs* m, uint64_t* out3);
 smb200_status smb200_crs_types(const smb200_crs* m, int32_t* vt, int32_t* it);

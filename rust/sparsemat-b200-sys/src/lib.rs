@@ -12,6 +12,7 @@ pub const SMB200_ERR_SIZE_MISMATCH: smb200_status = 5; // linearsolver.rs:33-36 
 pub const SMB200_ERR_NCCL: smb200_status = 6;
 pub const SMB200_ERR_UNSUPPORTED: smb200_status = 7;
 pub const SMB200_ERR_OOM: smb200_status = 8;
+pub const SMB200_ERR_IO: smb200_status = 9;            // crsfile_* / crs_save / crs_load
 
 pub const SMB200_F32: i32 = 0;
 pub const SMB200_F64: i32 = 1;
@@ -64,6 +65,13 @@ extern "C" {
                                      columns: *const c_void, values: *const c_void, pos_start: *const c_void,
                                      index_list: *const c_void, out: *mut *mut smb200_crs) -> smb200_status;
     pub fn smb200_crs_free(m: *mut smb200_crs) -> smb200_status;
+    pub fn smb200_crsfile_write(path: *const c_char, vt: i32, it: i32, n_rows: u64, n_cols: u64, nnz: u64,
+                                values: *const c_void, columns: *const c_void, offset_rows: *const c_void) -> smb200_status;
+    pub fn smb200_crsfile_info(path: *const c_char, vt: *mut i32, it: *mut i32, out3: *mut u64) -> smb200_status;
+    pub fn smb200_crsfile_read(path: *const c_char, values: *mut c_void, columns: *mut c_void,
+                               offset_rows: *mut c_void) -> smb200_status;
+    pub fn smb200_crs_save(m: *const smb200_crs, path: *const c_char) -> smb200_status;
+    pub fn smb200_crs_load(ctx: *mut smb200_ctx, path: *const c_char, out: *mut *mut smb200_crs) -> smb200_status;
     pub fn smb200_crs_dims(m: *const smb200_crs, out3: *mut u64) -> smb200_status;
     pub fn smb200_crs_download(m: *const smb200_crs, values: *mut c_void, columns: *mut c_void,
                                offset_rows: *mut c_void) -> smb200_status;

@@ -121,6 +121,21 @@ impl<T: GpuValue, I: GpuIndex> GpuCrs<T, I> {
         });
         GpuCrs { h, ctx: ctx.clone(), _t: PhantomData }
     }
+    /// Binary CRS container (additive; the reference only writes text/PBM, sparsematrix.rs:304-338).
+    pub fn save(&self, path: &std::path::Path) {
+        let c = std::ffi::CString::new(path.to_string_lossy().as_bytes()).expect("path contains NUL");
+        check(unsafe { sys::smb200_crs_save(self.h, c.as_ptr()) });
+    }
+    /// Panics if the file holds another value/index type than `T`/`I`, or is damaged.
+    pub fn load(ctx: &Context, path: &std::path::Path) -> Self {
+        let c = std::ffi::CString::new(path.to_string_lossy().as_bytes()).expect("path contains NUL");
+        let (mut vt, mut it) = (0i32, 0i32);
+        check(unsafe { sys::smb200_crsfile_info(c.as_ptr(), &mut vt, &mut it, ptr::null_mut()) });
+        assert!(vt == T::VT && it == I::IT, "GpuCrs::load: the file holds another value/index type");
+        let mut h = ptr::null_mut();
+        check(unsafe { sys::smb200_crs_load((ctx.0).0, c.as_ptr(), &mut h) });
+        GpuCrs { h, ctx: ctx.clone(), _t: PhantomData }
+    }
     fn dims(&self) -> [u64; 3] { let mut d = [0u64; 3]; check(unsafe { sys::smb200_crs_dims(self.h, d.as_mut_ptr()) }); d }
     pub fn n_rows(&self) -> usize { self.dims()[0] as usize }
     pub fn n_cols(&self) -> usize { self.dims()[1] as usize }

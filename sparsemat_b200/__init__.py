@@ -5,7 +5,7 @@ package is the thin Python mirror of the reference's interface used by the tests
 """
 from .api import (  # noqa: F401
     ConjugateGradient, Context, DenseVec, DistCRS, Event, Panic, SmbError, SparseMatCRS, SparseMatIndexList,
-    SparseMatPar, crs_from_indexlist_arrays, ghost_plan, partition_rows, partition_rows_by_nnz, pinned_empty,
+    SparseMatPar, crs_from_indexlist_arrays, crsfile_read, crsfile_write, ghost_plan, partition_rows, partition_rows_by_nnz, pinned_empty,
 )
 from ._ffi import (  # noqa: F401
     FLAG_L2_PERSIST_X, SPMV_AUTO, SPMV_BANDED, SPMV_RING, SPMV_SCALAR, SPMV_STREAM, SPMV_STREAM_PIPE, SPMV_STREAM_TMA, SPMV_VECTOR, VARIANT_NAMES,

@@ -14,7 +14,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libsmb200.so")
 
-OK, ERR_INVALID, ERR_DIM, ERR_CUDA, ERR_NOT_SQUARE, ERR_SIZE_MISMATCH, ERR_NCCL, ERR_UNSUPPORTED, ERR_OOM = range(9)
+OK, ERR_INVALID, ERR_DIM, ERR_CUDA, ERR_NOT_SQUARE, ERR_SIZE_MISMATCH, ERR_NCCL, ERR_UNSUPPORTED, ERR_OOM, ERR_IO = range(10)
 F32, F64 = 0, 1
 U32, U64 = 0, 1
 SPMV_AUTO, SPMV_SCALAR, SPMV_VECTOR, SPMV_STREAM, SPMV_STREAM_TMA, SPMV_BANDED, SPMV_STREAM_PIPE, SPMV_RING = range(8)
@@ -106,6 +106,11 @@ PROTOTYPES = {
     "smb200_crs_upload": (_i32, [_p, _i32, _i32, _u64, _u64, _u64, _p, _p, _p, _pp]),
     "smb200_crs_from_indexlist": (_i32, [_p, _i32, _i32, _u64, _u64, _u64, _p, _p, _p, _p, _pp]),
     "smb200_crs_free": (_i32, [_p]),
+    "smb200_crsfile_write": (_i32, [C.c_char_p, _i32, _i32, _u64, _u64, _u64, _p, _p, _p]),
+    "smb200_crsfile_info": (_i32, [C.c_char_p, C.POINTER(_i32), C.POINTER(_i32), _u64p]),
+    "smb200_crsfile_read": (_i32, [C.c_char_p, _p, _p, _p]),
+    "smb200_crs_save": (_i32, [_p, C.c_char_p]),
+    "smb200_crs_load": (_i32, [_p, C.c_char_p, _pp]),
     "smb200_crs_dims": (_i32, [_p, _u64p]),
     "smb200_crs_types": (_i32, [_p, C.POINTER(_i32), C.POINTER(_i32)]),
     "smb200_crs_download": (_i32, [_p, _p, _p, _p]),

@@ -13,6 +13,7 @@ Everything compute runs through libsmb200; nothing here computes on the CPU.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -247,6 +248,30 @@ class DenseVec:
 
 
 # --------------------------------------------------------------------------------------------------------------
+def crsfile_write(path, n_rows, n_cols, values, columns, offset_rows) -> None:
+    """Host only: write CRS arrays (sparsemat_crs.rs:9-17 layout) as a binary container.  No device needed."""
+    values = np.ascontiguousarray(values)
+    columns = np.ascontiguousarray(columns)
+    offset_rows = np.ascontiguousarray(offset_rows, columns.dtype)
+    check(lib.smb200_crsfile_write(os.fsencode(path), F.vtype_of(values.dtype), F.itype_of(columns.dtype), n_rows, n_cols,
+                                   values.size, F.ptr(values) if values.size else None, F.ptr(columns) if columns.size else None,
+                                   F.ptr(offset_rows) if n_rows else None))
+
+
+def crsfile_read(path):
+    """Host only: (n_rows, n_cols, values, columns, offset_rows) of a binary CRS container; raises SmbError(ERR_IO) for
+    foreign, truncated or damaged files."""
+    vt, it = C.c_int32(), C.c_int32()
+    d = (C.c_uint64 * 3)()
+    check(lib.smb200_crsfile_info(os.fsencode(path), C.byref(vt), C.byref(it), d))
+    values = np.empty(d[2], F.VDTYPES[vt.value])
+    columns = np.empty(d[2], F.IDTYPES[it.value])
+    offsets = np.empty(d[0] + 1 if d[0] else 0, F.IDTYPES[it.value])
+    check(lib.smb200_crsfile_read(os.fsencode(path), F.ptr(values) if values.size else None, F.ptr(columns) if columns.size else None,
+                                  F.ptr(offsets) if offsets.size else None))
+    return int(d[0]), int(d[1]), values, columns, offsets
+
+
 class SparseMatCRS:
     """sparsemat_crs.rs:9-17 on the device; ``mvp`` is sparsematrix.rs:146-158."""
 
@@ -293,6 +318,17 @@ class SparseMatCRS:
         check(lib.smb200_gen_powerlaw(ctx._h, F.vtype_of(dtype), F.itype_of(itype), n_rows, n_cols or n_rows, seed_len,
                                       seed_col, seed_val, max_len, C.byref(h)))
         return cls(ctx, h)
+
+    @classmethod
+    def load(cls, ctx, path) -> "SparseMatCRS":
+        """Read a binary CRS container written by ``save`` / ``crsfile_write`` and upload it (validated like any upload)."""
+        h = C.c_void_p()
+        check(lib.smb200_crs_load(ctx._h, os.fsencode(path), C.byref(h)))
+        return cls(ctx, h)
+
+    def save(self, path) -> None:
+        """Download the three CRS arrays and write them, byte for byte, behind a checksummed header (include/smb200.h)."""
+        check(lib.smb200_crs_save(self._h, os.fsencode(path)))
 
     def _dims(self):
         d = (C.c_uint64 * 3)()

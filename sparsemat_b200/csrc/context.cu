@@ -169,7 +169,7 @@ smb200_status smb200_ctx_devinfo(smb200_ctx* ctx, smb200_devinfo* out) {
     out->l2_bytes = prop.l2CacheSize;
     out->l2_persist_max_bytes = prop.persistingL2CacheMaxSize;
     out->hbm_bytes = (int64_t)prop.totalGlobalMem;
-    strncpy(out->name, prop.name, sizeof out->name - 1);
+    snprintf(out->name, sizeof out->name, "%.*s", (int)sizeof out->name - 1, prop.name);
     return SMB200_OK;
 }
 

@@ -130,6 +130,17 @@ public:
                                 columns.data(), offset_rows.data(), &m));
         return SparseMatCRS(ctx, m);
     }
+    // Binary CRS container (additive: the reference has text/PBM writers only, sparsematrix.rs:304-338): the three arrays
+    // byte for byte behind a checksummed header.  load() refuses files of another value/index type.
+    void save(const std::string& path) const { check(smb200_crs_save(raw(), path.c_str())); }
+    static SparseMatCRS load(const Context& ctx, const std::string& path) {
+        int32_t vt = 0, it = 0;
+        check(smb200_crsfile_info(path.c_str(), &vt, &it, nullptr));
+        if (vt != (int32_t)vtype_of<T>() || it != (int32_t)itype_of<I>()) throw Panic("SparseMatCRS::load: the file holds another value/index type");
+        smb200_crs* m = nullptr;
+        check(smb200_crs_load(ctx.get(), path.c_str(), &m));
+        return SparseMatCRS(ctx, m);
+    }
     uint64_t n_rows() const { return dims()[0]; }
     uint64_t n_cols() const { return dims()[1]; }
     uint64_t n_non_zero_entries() const { return dims()[2]; }

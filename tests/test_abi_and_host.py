@@ -160,3 +160,51 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d["value"] > 0 and d["config"]["nnz"] == 117_047_296 and d["dtype"] == "f32"
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["serial_value"] > 0
     assert d["e2e"] == {"value": d["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_binary_crs_container_round_trip_and_damage(tmp_path):
+    """smb200_crsfile_* (host only): the three arrays of SparseMatCRS (sparsemat_crs.rs:9-17) survive byte for byte for every
+    type combination, ragged and empty shapes included; foreign, truncated and bit-flipped files are refused with ERR_IO."""
+    import sparsemat_b200 as smb
+    from sparsemat_b200 import _ffi as F
+    rng = np.random.default_rng(5)
+    for k, (vdt, idt) in enumerate([(np.float32, np.uint32), (np.float64, np.uint32), (np.float32, np.uint64), (np.float64, np.uint64)]):
+        for n_rows, n_cols, max_len in [(37, 23, 6), (1, 1, 1), (5, 9, 0), (1000, 1000, 40)]:
+            lens = rng.integers(0, max_len + 1, n_rows)
+            offs = np.zeros(n_rows + 1, idt)
+            offs[1:] = np.cumsum(lens)
+            nnz = int(offs[-1])
+            cols = rng.integers(0, n_cols, nnz).astype(idt)                   # unsorted inside a row, duplicates allowed
+            vals = rng.uniform(-1, 1, nnz).astype(vdt)
+            path = tmp_path / f"m{k}_{n_rows}.smbcrs"
+            smb.crsfile_write(path, n_rows, n_cols, vals, cols, offs)
+            assert os.path.getsize(path) == 56 + sum((a.nbytes + 7) // 8 * 8 for a in (offs, cols, vals))
+            r, c, v2, c2, o2 = smb.crsfile_read(path)
+            assert (r, c) == (n_rows, n_cols)
+            assert v2.dtype == vals.dtype and c2.dtype == cols.dtype and o2.dtype == offs.dtype
+            assert v2.tobytes() == vals.tobytes() and np.array_equal(c2, cols) and np.array_equal(o2, offs)
+    # the 0 x 0 matrix (SparseMatCRS::new(), what to_crs gives for an empty IndexList): header only
+    empty = tmp_path / "empty.smbcrs"
+    smb.crsfile_write(empty, 0, 0, np.empty(0, np.float64), np.empty(0, np.uint32), np.empty(0, np.uint32))
+    assert os.path.getsize(empty) == 56
+    r, c, v2, c2, o2 = smb.crsfile_read(empty)
+    assert (r, c, v2.size, c2.size, o2.size) == (0, 0, 0, 0, 0)
+    # damage
+    good = (tmp_path / "m0_37.smbcrs").read_bytes()
+
+    def refused(data, what):
+        bad = tmp_path / "bad.smbcrs"
+        bad.write_bytes(data)
+        with pytest.raises(smb.SmbError) as e:
+            smb.crsfile_read(bad)
+        assert e.value.status == F.ERR_IO and what in str(e.value), (what, str(e.value))
+
+    refused(b"NOTACRS!" + good[8:], "not a SMBCRS01 file")
+    refused(good[:40], "shorter than a header")
+    refused(good[:-9], "truncated")
+    flipped = bytearray(good)
+    flipped[-13] ^= 0x10                                                      # one bit inside the values (the last 4 bytes are padding)
+    refused(bytes(flipped), "checksum mismatch")
+    with pytest.raises(smb.SmbError) as e:
+        smb.crsfile_read(tmp_path / "does_not_exist.smbcrs")
+    assert e.value.status == F.ERR_IO

@@ -77,6 +77,45 @@ def test_to_crs_edge_cases(smb, orc, ctx):
         smb.crs_from_indexlist_arrays(ctx, 6, 10, cols, vals, pos, bad)
 
 
+def test_binary_crs_container_through_the_device(smb, orc, ctx, tmp_path):
+    """README workflow with a file in between: assemble in IndexList order -> to_crs on the device -> save; a later run loads
+    the file and gets the same three arrays bit for bit (in-row insertion order included) and the same product; a file written
+    on the host alone (crsfile_write) loads too; a file whose arrays are not a CRS matrix is refused by the upload validation."""
+    rng = np.random.default_rng(8)
+    for vdt, idt in [(np.float32, np.uint32), (np.float64, np.uint64)]:
+        sp = smb.SparseMatIndexList(vdt, idt)
+        i, j = rng.integers(0, 500, 4000), rng.integers(0, 700, 4000)
+        sp.set(i, j, rng.uniform(-1, 1, 4000).astype(vdt))
+        a = sp.to_crs(ctx)
+        path = tmp_path / f"a_{np.dtype(vdt).name}.smbcrs"
+        a.save(path)
+        b = smb.SparseMatCRS.load(ctx, path)
+        assert (b.n_rows(), b.n_cols(), b.n_non_zero_entries()) == (a.n_rows(), a.n_cols(), a.n_non_zero_entries())
+        assert b.dtype == a.dtype and b.itype == a.itype
+        for got, want in zip(b.raw_parts(), a.raw_parts()):
+            assert got.tobytes() == want.tobytes()
+        x = rng.uniform(-1, 1, a.n_cols()).astype(vdt)
+        xd = smb.DenseVec.from_vec(ctx, x)
+        assert np.array_equal(b.mvp(xd).to_numpy(), a.mvp(xd).to_numpy())
+        # the host-only reader sees what the device wrote
+        n_rows, n_cols, v, c, o = smb.crsfile_read(path)
+        assert (n_rows, n_cols) == (a.n_rows(), a.n_cols()) and np.array_equal(orc.mvp(v, c, o, x), a.mvp(xd).to_numpy())
+    # the 0 x 0 matrix
+    e = smb.SparseMatIndexList(np.float64, np.uint32).to_crs(ctx)
+    e.save(tmp_path / "e.smbcrs")
+    assert smb.SparseMatCRS.load(ctx, tmp_path / "e.smbcrs").n_rows() == 0
+    # host-written file -> device
+    vals, cols, offs = orc.laplace(np.float64, np.uint32, 9, 7, 5)
+    smb.crsfile_write(tmp_path / "lap.smbcrs", 315, 315, vals, cols, offs)
+    lap = smb.SparseMatCRS.load(ctx, tmp_path / "lap.smbcrs")
+    x = orc.uniform(np.float64, 3, 315)
+    assert np.array_equal(lap.mvp(smb.DenseVec.from_vec(ctx, x)).to_numpy(), orc.mvp(vals, cols, offs, x))
+    # a well-formed container around arrays that are not a CRS matrix (a column >= n_cols)
+    smb.crsfile_write(tmp_path / "bad.smbcrs", 315, 100, vals, cols, offs)
+    with pytest.raises(smb.SmbError):
+        smb.SparseMatCRS.load(ctx, tmp_path / "bad.smbcrs")
+
+
 # ---- (b) CG -----------------------------------------------------------------------------------------------
 def test_reference_cg_known_answer(smb, ctx):
     """lib.rs:36-52: [[4,1],[1,3]] x = [1,2], x0 = [2,1], default solver -> x[0] floors to 0.0909."""
