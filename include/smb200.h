@@ -62,13 +62,21 @@ typedef enum {
     SMB200_SPMV_STREAM_PIPE = 6, /* K3 persistent: one CTA per SM slot walks its row blocks through a
                                 multi-stage shared-memory ring filled by cp.async.bulk (TMA) + mbarrier,
                                 so the HBM stream never waits for the gather / row-sum phases         */
-    SMB200_SPMV_RING = 7     /* K4 persistent, short rows (<= 32 entries: stencils, FEM): values, columns, row
+    SMB200_SPMV_RING = 7,    /* K4 persistent, short rows (<= 32 entries: stencils, FEM): values, columns, row
                                 offsets and the block's x segments (up to 4 windows found at plan time) are
                                 ALL staged by TMA into a shared-memory ring by a producer warp; consumer warps
                                 sum one row per thread in storage order (bit-exact) with no block barrier.
                                 Blocks without windows gather x from global memory.  Falls back to STREAM
                                 when the matrix has longer rows.  AUTO picks it when >= 80 % of the blocks
                                 have windows                                                           */
+    SMB200_SPMV_BANDSPLIT = 8 /* x larger than L2, scattered columns (power-law / graph matrices): at plan time the
+                                matrix is cut into column bands of about half an L2 of x each (same rows, storage
+                                order kept inside a band, columns rebased to the band -> u32); one STREAM launch
+                                per band, the first writes y, the others add to it, so the gathers of a launch
+                                hit a cache-resident band.  Rows are summed band-major: tolerance-exact, not
+                                bit-exact.  Whole-matrix products only (row ranges fall back to STREAM).
+                                EXPERIMENTAL in this round: opt-in, AUTO picks it only under
+                                SMB200_BANDSPLIT_AUTO=1                                                   */
 } smb200_spmv_variant;
 
 /* flags for smb200_crs_configure */

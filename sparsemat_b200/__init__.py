@@ -8,7 +8,7 @@ from .api import (  # noqa: F401
     SparseMatPar, crs_from_indexlist_arrays, crsfile_read, crsfile_write, ghost_plan, partition_rows, partition_rows_by_nnz, pinned_empty,
 )
 from ._ffi import (  # noqa: F401
-    FLAG_L2_PERSIST_X, SPMV_AUTO, SPMV_BANDED, SPMV_RING, SPMV_SCALAR, SPMV_STREAM, SPMV_STREAM_PIPE, SPMV_STREAM_TMA, SPMV_VECTOR, VARIANT_NAMES,
+    FLAG_L2_PERSIST_X, SPMV_AUTO, SPMV_BANDED, SPMV_BANDSPLIT, SPMV_RING, SPMV_SCALAR, SPMV_STREAM, SPMV_STREAM_PIPE, SPMV_STREAM_TMA, SPMV_VECTOR, VARIANT_NAMES,
 )
 
 __version__ = "0.1.0"

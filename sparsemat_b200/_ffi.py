@@ -17,9 +17,9 @@ LIB_PATH = os.path.join(_HERE, "lib", "libsmb200.so")
 OK, ERR_INVALID, ERR_DIM, ERR_CUDA, ERR_NOT_SQUARE, ERR_SIZE_MISMATCH, ERR_NCCL, ERR_UNSUPPORTED, ERR_OOM, ERR_IO = range(10)
 F32, F64 = 0, 1
 U32, U64 = 0, 1
-SPMV_AUTO, SPMV_SCALAR, SPMV_VECTOR, SPMV_STREAM, SPMV_STREAM_TMA, SPMV_BANDED, SPMV_STREAM_PIPE, SPMV_RING = range(8)
+SPMV_AUTO, SPMV_SCALAR, SPMV_VECTOR, SPMV_STREAM, SPMV_STREAM_TMA, SPMV_BANDED, SPMV_STREAM_PIPE, SPMV_RING, SPMV_BANDSPLIT = range(9)
 FLAG_L2_PERSIST_X = 1
-VARIANT_NAMES = {0: "auto", 1: "scalar", 2: "vector", 3: "stream", 4: "stream_tma", 5: "banded", 6: "stream_pipe", 7: "ring"}
+VARIANT_NAMES = {0: "auto", 1: "scalar", 2: "vector", 3: "stream", 4: "stream_tma", 5: "banded", 6: "stream_pipe", 7: "ring", 8: "bandsplit"}
 
 
 class Panic(RuntimeError):

@@ -106,6 +106,9 @@ struct smb200_event {
 namespace smb {
 
 // ---- SpMV plan: built once per matrix (and per variant) -------------------------------------------
+}  // namespace smb
+struct smb200_crs;
+namespace smb {
 struct SpmvPlan {
     int variant = SMB200_SPMV_AUTO;     // resolved
     int lanes = 0;
@@ -128,6 +131,10 @@ struct SpmvPlan {
     unsigned cap = 0, target = 0;       // STREAM*: staging capacity / merge target the plan was cut for (elements)
     void* blk_win = nullptr;            // BANDED: [2*n_blocks] (cmin, cmax+1) per block, index type
     uint64_t max_win = 0;               // BANDED: widest window (elements)
+    // BANDSPLIT: the matrix cut into column bands of band_width elements, each an ordinary CRS matrix (same rows, columns
+    // rebased to its band) with its own stream plan; owned by the plan
+    std::vector<smb200_crs*> parts;
+    uint64_t band_width = 0;
     bool built = false;
 };
 
@@ -190,6 +197,8 @@ extern thread_local int g_ring_reserve_sms;
 // Upper bound on the CTAs of a persistent (ring) launch (0 = none): boundary-row launches that run beside the interior
 // kernel use as many CTAs as it left slots, each walking several blocks through its ring.
 extern thread_local int g_ring_grid_cap;
+// Set while the second and later bands of a band-split product are launched: the stream kernel adds to y instead of writing it.
+extern thread_local bool g_spmv_accumulate;
 // Set while an SpMV reads a caller-owned (smb200_vec_wrap) vector: such memory has no padding behind its last element,
 // so kernels must not round bulk copies of it up to 16 bytes.
 extern thread_local bool g_x_unpadded;
@@ -206,6 +215,8 @@ smb200_status plan_build(smb200_crs* m);
 smb200_status plan_build_range(smb200_crs* m, SpmvPlan& p, int want_variant, int want_lanes, uint32_t flags,
                                uint64_t row_begin, uint64_t row_end);
 void plan_free(SpmvPlan& p);
+smb200_status bandsplit_build(smb200_crs* m, SpmvPlan& p, int fallback_variant);      // bandsplit.cu
+uint64_t bandsplit_stream_bytes(const smb200_crs* m, const SpmvPlan& p);
 void hostpipe_free(HostPipe& hp);
 void cg_free(CgWork& w);
 smb200_status spmv_launch_plan(smb200_crs* m, const SpmvPlan& p, uint64_t row_begin, uint64_t row_end, const void* x,

@@ -59,6 +59,14 @@ template <class T> __device__ __forceinline__ T warp_sum_t(T v) {
     return v;
 }
 
+// y[r] = sum, or y[r] += sum for the second and later column bands of a band-split product (BANDSPLIT); returns what was
+// stored (the fused dot weighs the final value).
+template <class T> __device__ __forceinline__ T store_y(T* __restrict__ y, uint64_t r, T sum, bool accumulate) {
+    if (accumulate) sum = add_rn(y[r], sum);
+    y[r] = sum;
+    return sum;
+}
+
 // Fused dot epilogue of the SpMV kernels: every CTA leaves ONE f64 partial; spmv_dot_finalize_kernel (launched
 // right behind on the same stream) folds them in index order.  No ticket atomics and no __threadfence in the hot
 // kernel: with ~40k CTAs a single-address ticket costs more than a quarter of the product itself (measured).
@@ -161,7 +169,7 @@ template <class E> __device__ __forceinline__ void store_quad_shared(E* p, const
 template <class T, class I, bool DOT, int THREADS = kSpmvThreads>
 __device__ __forceinline__ double reduce_rows_from_smem(const T* prod, const I* __restrict__ offs, uint64_t r0, uint64_t r1,
                                                         uint64_t a0, T* __restrict__ y, const T* __restrict__ w,
-                                                        unsigned int* s_long_count, unsigned int* s_long_rows) {
+                                                        unsigned int* s_long_count, unsigned int* s_long_rows, bool accumulate = false) {
     double acc = 0.0;
     for (uint64_t r = r0 + threadIdx.x; r < r1; r += THREADS) {
         const unsigned a = (unsigned)((uint64_t)__ldg(offs + r) - a0);
@@ -169,7 +177,7 @@ __device__ __forceinline__ double reduce_rows_from_smem(const T* prod, const I* 
         if (e - a <= (unsigned)kWarpRowMin) {
             T s = T(0);
             for (unsigned k = a; k < e; ++k) s = add_rn(s, prod[k]);
-            y[r] = s;
+            s = store_y(y, r, s, accumulate);
             if constexpr (DOT) acc += (double)mul_rn(__ldg(w + r), s);
         } else {
             const unsigned slot = atomicAdd(s_long_count, 1u);
@@ -187,7 +195,7 @@ __device__ __forceinline__ double reduce_rows_from_smem(const T* prod, const I* 
         for (unsigned k = a + lane; k < e; k += 32) s = add_rn(s, prod[k]);
         s = warp_sum_t(s);
         if (lane == 0) {
-            y[r] = s;
+            s = store_y(y, r, s, accumulate);
             if constexpr (DOT) acc += (double)mul_rn(__ldg(w + r), s);
         }
     }
@@ -200,7 +208,7 @@ template <class T, class I, bool DOT, int THREADS = kSpmvThreads>
 __device__ __forceinline__ double rows_direct(const T* __restrict__ vals, const I* __restrict__ cols, const I* __restrict__ offs,
                                               uint64_t r0, uint64_t r1, const T* __restrict__ x, T* __restrict__ y,
                                               const T* __restrict__ w, unsigned int* s_long_count, unsigned int* s_long_rows,
-                                              double* scratch) {
+                                              double* scratch, bool accumulate = false) {
     double acc = 0.0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (uint64_t r = r0 + warp; r < r1; r += THREADS / 32) {
@@ -216,7 +224,7 @@ __device__ __forceinline__ double rows_direct(const T* __restrict__ vals, const 
         for (uint64_t k = a + lane; k < e; k += 32) s = add_rn(s, mul_rn(__ldg(x + (size_t)__ldcs(cols + k)), __ldcs(vals + k)));
         s = warp_sum_t(s);
         if (lane == 0) {
-            y[r] = s;
+            s = store_y(y, r, s, accumulate);
             if constexpr (DOT) acc += (double)mul_rn(__ldg(w + r), s);
         }
     }
@@ -236,8 +244,7 @@ __device__ __forceinline__ double rows_direct(const T* __restrict__ vals, const 
         if (k < e) s0 = add_rn(s0, mul_rn(__ldg(x + (size_t)__ldcs(cols + k)), __ldcs(vals + k)));
         const double tot = block_sum<THREADS>((double)s0 + (double)s1, scratch);
         if (threadIdx.x == 0) {
-            const T s = (T)tot;
-            y[r] = s;
+            const T s = store_y(y, r, (T)tot, accumulate);
             if constexpr (DOT) acc += (double)mul_rn(__ldg(w + r), s);
         }
     }
@@ -249,7 +256,7 @@ template <class T, class I, bool DOT>
 __global__ void __launch_bounds__(kSpmvThreads, sizeof(T) == 4 ? 8 : 6)
 spmv_stream_kernel(const T* __restrict__ vals, const I* __restrict__ cols, const I* __restrict__ offs,
                    const I* __restrict__ blk_rows, const I* __restrict__ blk_nnz, unsigned cap, const T* __restrict__ x,
-                   T* __restrict__ y, DotArgs dot) {
+                   T* __restrict__ y, DotArgs dot, int accumulate) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     T* prod = reinterpret_cast<T*>(smem_raw);
     __shared__ unsigned int s_long_count;
@@ -315,10 +322,12 @@ spmv_stream_kernel(const T* __restrict__ vals, const I* __restrict__ cols, const
         uint64_t r_next = r0;
         bool all_short = true;
         double acc_fast = 0.0;
+        // (accumulate mode — y += — skips this pass: a block that is redone generically below would add its rows twice)
+        if (accumulate) all_short = false;
 #pragma unroll
         for (int j = 0; j < KP; ++j) {
             const uint64_t r = r0 + threadIdx.x + (uint64_t)j * kSpmvThreads;
-            if (r < r1) {
+            if (r < r1 && !accumulate) {
                 const unsigned a = (unsigned)((uint64_t)pfa[j] - a0), e = (unsigned)((uint64_t)pfe[j] - a0);
                 if (e - a <= (unsigned)kWarpRowMin) {
                     T sum = T(0);
@@ -335,9 +344,9 @@ spmv_stream_kernel(const T* __restrict__ vals, const I* __restrict__ cols, const
         if (__syncthreads_or(!all_short)) { r_next = r0; acc_fast = 0.0; }    // redo the block generically
         acc = acc_fast;
         if (r_next < r1)
-            acc += reduce_rows_from_smem<T, I, DOT>(prod, offs, r_next, r1, a0 + 0, y, (const T*)dot.w, &s_long_count, s_long_rows);
+            acc += reduce_rows_from_smem<T, I, DOT>(prod, offs, r_next, r1, a0 + 0, y, (const T*)dot.w, &s_long_count, s_long_rows, accumulate != 0);
     } else {
-        acc = rows_direct<T, I, DOT>(vals, cols, offs, r0, r1, x, y, (const T*)dot.w, &s_long_count, s_long_rows, scratch);
+        acc = rows_direct<T, I, DOT>(vals, cols, offs, r0, r1, x, y, (const T*)dot.w, &s_long_count, s_long_rows, scratch, accumulate != 0);
     }
     if constexpr (DOT) finish_dot<T>(acc, dot);
 }
@@ -1131,6 +1140,7 @@ void plan_free(SpmvPlan& p) {
     if (p.lcols) cudaFree(p.lcols);
     if (p.loffs) cudaFree(p.loffs);
     if (p.blk_win) cudaFree(p.blk_win);
+    for (smb200_crs* part : p.parts) smb200_crs_free(part);
     p = SpmvPlan();
 }
 
@@ -1206,6 +1216,10 @@ smb200_status plan_build_range(smb200_crs* m, SpmvPlan& p, int want_variant, int
         SMB_TRY(plan_build_range_impl(m, p, SMB200_SPMV_RING, want_lanes, flags, rb, re));
         if (p.variant == SMB200_SPMV_RING && p.n_xwin * 10 >= p.n_blocks * 8) return SMB200_OK;
     }
+    // EXPERIMENTAL, opt-in: x far larger than L2 and long/irregular rows (the ring was not kept) -> column bands
+    if (want == SMB200_SPMV_AUTO && env_int("SMB200_BANDSPLIT_AUTO", 0) != 0 && rb == 0 && re == m->n_rows && m->x_extra == 0 &&
+        m->n_cols * vsize(m->vt) > 2 * (uint64_t)m->ctx->l2_bytes && m->nnz >= 4 * m->n_rows)
+        return plan_build_range_impl(m, p, SMB200_SPMV_BANDSPLIT, want_lanes, flags, rb, re);
     return plan_build_range_impl(m, p, want_variant, want_lanes, flags, rb, re);
 }
 
@@ -1398,6 +1412,14 @@ static smb200_status plan_build_range_impl(smb200_crs* m, SpmvPlan& p, int want_
     }
     // RING needs short rows everywhere (its stages have no long-row path)
     if (variant == SMB200_SPMV_RING && m->max_row_len > (uint64_t)kRowMajorMax) variant = SMB200_SPMV_STREAM;
+    if (variant == SMB200_SPMV_BANDSPLIT) {
+        // whole-matrix products only; a matrix of a single band (or a row range, or a distributed block) is STREAM's
+        if (rb == 0 && re == m->n_rows && m->x_extra == 0 && rows > 0) {
+            SMB_TRY(bandsplit_build(m, p, SMB200_SPMV_STREAM));
+            if (p.variant == SMB200_SPMV_BANDSPLIT) { p.built = true; return SMB200_OK; }
+        }
+        variant = SMB200_SPMV_STREAM;
+    }
     p.variant = variant;
     p.lanes = 0;
     if (variant == SMB200_SPMV_SCALAR) p.lanes = 1;
@@ -1504,7 +1526,8 @@ static smb200_status launch_typed(smb200_crs* m, const SpmvPlan& p, uint64_t rb,
             auto kern = spmv_stream_kernel<T, I, DOT>;
             if (smem > 32 * 1024) SMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             if (carve >= 0) SMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-            kern<<<(unsigned)p.n_blocks, kSpmvThreads, smem, st>>>(vals, cols, offs, (const I*)p.blk_rows, (const I*)p.blk_nnz, sh.cap, xx, yy, dot);
+            kern<<<(unsigned)p.n_blocks, kSpmvThreads, smem, st>>>(vals, cols, offs, (const I*)p.blk_rows, (const I*)p.blk_nnz, sh.cap, xx, yy, dot,
+                                                                   g_spmv_accumulate ? 1 : 0);
         } else if (p.variant == SMB200_SPMV_RING) {
             // bulk copies need 16-byte aligned sources whose rounded-up tails stay inside the allocation
             const int xwin_ok = (((uintptr_t)x & 15u) == 0 && !g_x_unpadded && env_int("SMB200_RING_XWIN", 1) != 0) ? 1 : 0;
@@ -1630,6 +1653,21 @@ static smb200_status spmv_launch_impl(smb200_crs* m, const SpmvPlan& p, uint64_t
                                       const void* w, double* result, double* roll_dst, const double* roll_src,
                                       const double* done) {
     if (re <= rb) return SMB200_OK;
+    if (p.variant == SMB200_SPMV_BANDSPLIT) {
+        // y = sum_b A_b x_b: one launch per column band; the first writes y, the others add; the fused dot (and the CG
+        // roll) ride the last one, which stores the final y
+        const size_t es = vsize(m->vt);
+        for (size_t b = 0; b < p.parts.size(); ++b) {
+            smb200_crs* part = p.parts[b];
+            const bool last = b + 1 == p.parts.size();
+            g_spmv_accumulate = b > 0;
+            const smb200_status st = spmv_launch_impl(part, part->plan, 0, part->n_rows, (const char*)x + b * (size_t)p.band_width * es, y,
+                                                      last ? w : nullptr, result, last ? roll_dst : nullptr, roll_src, done);
+            g_spmv_accumulate = false;
+            SMB_TRY(st);
+        }
+        return SMB200_OK;
+    }
     smb200_ctx* ctx = m->ctx;
     DotArgs dot{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     if (w) {
@@ -1683,13 +1721,15 @@ extern "C" {
 
 smb200_status smb200_crs_configure(smb200_crs* m, smb200_spmv_variant variant, int32_t lanes, uint32_t flags) {
     SMB_REQUIRE(m, SMB200_ERR_INVALID, "crs_configure: NULL argument");
-    SMB_REQUIRE(variant >= SMB200_SPMV_AUTO && variant <= SMB200_SPMV_RING, SMB200_ERR_INVALID, "crs_configure: bad variant %d", (int)variant);
+    SMB_REQUIRE(variant >= SMB200_SPMV_AUTO && variant <= SMB200_SPMV_BANDSPLIT, SMB200_ERR_INVALID, "crs_configure: bad variant %d", (int)variant);
     m->want_variant = variant;
     m->want_lanes = lanes;
     m->want_flags = flags;
     cudaStreamSynchronize(m->ctx->stream);
     plan_free(m->plan);
     hostpipe_free(m->hp);
+    // a captured batch of CG iterations holds the old plan's arrays
+    if (m->cg.graph) { cudaGraphExecDestroy(m->cg.graph); m->cg.graph = nullptr; }
     if (m->n_rows == 0) return SMB200_OK;
     return plan_build(m);
 }
@@ -1710,11 +1750,12 @@ smb200_status smb200_crs_plan_info(const smb200_crs* cm, smb200_plan_info* out) 
     out->mean_row_len = m->n_rows ? (double)m->nnz / (double)m->n_rows : 0.0;
     out->algorithmic_bytes = m->nnz * (vsize(m->vt) + isize(m->it)) + (m->n_rows + 1) * isize(m->it) +
                              m->n_cols * vsize(m->vt) + m->n_rows * vsize(m->vt);
-    out->launches_per_spmv = 1;
+    out->launches_per_spmv = m->plan.variant == SMB200_SPMV_BANDSPLIT ? m->plan.parts.size() : 1;
     out->n_xwin_blocks = m->plan.n_xwin;
     out->nnz_c16 = m->plan.n_c16;
     out->rows_o16 = m->plan.n_o16;
     out->stream_bytes = out->algorithmic_bytes - (m->plan.n_c16 + m->plan.n_o16) * (isize(m->it) - 2);
+    if (m->plan.variant == SMB200_SPMV_BANDSPLIT) out->stream_bytes = bandsplit_stream_bytes(m, m->plan);
     return SMB200_OK;
 }
 

@@ -311,3 +311,59 @@ def test_small_matrix_sweep_all_variants_types_and_entry_points():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     res = subprocess.run([sys.executable, os.path.join(root, "scripts", "sanitize_small.py")], capture_output=True, text=True, timeout=600)
     assert res.returncode == 0 and "sanitize_small: ok" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
+
+
+@pytest.mark.parametrize("vdt,idt", COMBOS)
+def test_bandsplit_column_bands(smb, orc, ctx, vdt, idt):
+    """BANDSPLIT (experimental, opt-in): the matrix is cut into column bands at plan time and multiplied band by band, the
+    first launch writing y and the others adding to it.  Tiny bands are forced here so that small matrices split into many.
+    Band-major row sums: within the north-star tolerance of the oracle (not bit-exact); a row whose entries all fall into one
+    band IS bit-exact; fused dot and CG ride the last band."""
+    import os
+    tol = cases.TOL[np.dtype(vdt)]
+    try:
+        for width, case in [(1024, cases.ragged(51, 3000, 5000, 30, vdt, idt)), (2048, cases.powerlaw(52, 4000, 9000, 3000, vdt, idt)),
+                            (1024, cases.giant_row(53, 300, 20000, 30000, vdt, idt)), (1024, cases.all_empty(40, 5000, vdt, idt)),
+                            (4096, cases.banded(54, 9000, 50, 9, vdt, idt))]:
+            os.environ["SMB200_BANDSPLIT_WIDTH"] = str(width)
+            n_rows, n_cols, vals, cols, offs = case
+            a = smb.SparseMatCRS.from_raw_parts(ctx, *case).configure(smb.SPMV_BANDSPLIT)
+            info = a.plan_info()
+            if vals.size == 0:
+                assert info["variant"] == smb.SPMV_STREAM                                  # nothing to split
+            else:
+                assert info["variant"] == smb.SPMV_BANDSPLIT and info["launches_per_spmv"] == -(-n_cols // width), info
+            x = np.random.default_rng(7).uniform(-1, 1, n_cols).astype(vdt)
+            xd = smb.DenseVec.from_vec(ctx, x)
+            want = orc.mvp(vals, cols, offs, x)
+            y = smb.DenseVec(ctx, n_rows, vdt)
+            y.fill(123.0)                                                                  # the first band must overwrite, not add
+            got = a.mvp(xd, out=y).to_numpy()
+            scale = cases.abs_rowsum(vals, cols, offs, x) + np.finfo(np.float64).tiny
+            err = np.abs(got.astype(np.float64) - want.astype(np.float64)) / scale
+            assert np.all(np.isfinite(got)) and float(err.max(initial=0.0)) <= tol, (width, float(err.max(initial=0.0)))
+            assert np.array_equal(a.mvp(xd).to_numpy(), got)                               # deterministic
+            lhs = np.random.default_rng(8).uniform(-1, 1, n_rows).astype(vdt)
+            bil = float(a.inner_prod(smb.DenseVec.from_vec(ctx, lhs), xd))
+            ref = float(np.sum(lhs.astype(np.float64) * want.astype(np.float64)))
+            assert abs(bil - ref) <= 1e-5 * float(np.sum(np.abs(lhs.astype(np.float64)) * scale)) + 1e-30
+        # the banded case: every row lives in one or two bands -> rows inside one band are bit-exact
+        one_band = (cols.astype(np.int64) // width)
+        o = offs.astype(np.int64)
+        single = np.array([o[r] == o[r + 1] or one_band[o[r]:o[r + 1]].min() == one_band[o[r]:o[r + 1]].max() for r in range(n_rows)])
+        assert single.sum() > n_rows // 2 and np.array_equal(got[single], want[single])
+        # CG through the band-split product (f64 only: the solver's tolerance)
+        if vdt == np.float64:
+            os.environ["SMB200_BANDSPLIT_WIDTH"] = "1024"
+            lap = smb.SparseMatCRS.laplace(ctx, vdt, idt, 16, 16, 16).configure(smb.SPMV_BANDSPLIT)
+            assert lap.plan_info()["variant"] == smb.SPMV_BANDSPLIT and lap.plan_info()["launches_per_spmv"] == 4
+            v64, c64, o64 = orc.laplace(vdt, idt, 16, 16, 16)
+            b_host = orc.uniform(vdt, 6, 4096)
+            xs = smb.DenseVec(ctx, 4096, vdt)
+            st = smb.ConjugateGradient(1e-10, 500).solve_with_stats(lap, smb.DenseVec.from_vec(ctx, b_host), xs)
+            xo = np.zeros(4096)
+            so = orc.cg(4096, 4096, v64, c64, o64, b_host, xo, tol=1e-10, iter_max=500)
+            assert st["converged"] and abs(int(st["iterations"]) - so["iterations"]) <= 2, (st, so)
+            assert np.allclose(xs.to_numpy(), xo, rtol=1e-8, atol=1e-10)
+    finally:
+        os.environ.pop("SMB200_BANDSPLIT_WIDTH", None)
