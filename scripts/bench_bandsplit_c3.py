@@ -54,3 +54,7 @@ for w in widths:
     got = run(f"bandsplit width={w or 'L2/2'} (plan {dt:.2f} s)")
     d = np.abs(got - ref)
     print(f"    max |diff| vs stream {d.max():.3e}, max |y| {np.abs(ref).max():.3e}", flush=True)
+# the same with an L2 persisting window over the band of x that is being gathered
+os.environ.pop("SMB200_BANDSPLIT_WIDTH", None)
+a.configure(smb.SPMV_BANDSPLIT, 0, smb.FLAG_L2_PERSIST_X)
+run("bandsplit L2/2 + persisting x")
