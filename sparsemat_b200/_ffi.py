@@ -54,7 +54,7 @@ class CgStats(C.Structure):
 def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
-            f"{LIB_PATH} not found: build it with `python -m sparsemat_b200.build` (nvcc, sm_100a). "
+            f"{LIB_PATH} not found: build it with `make -C sparsemat_b200/csrc` or `python __graft_entry__.py` (nvcc, sm_100a). "
             "sparsemat_b200 has no CPU fallback.")
     return C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
 

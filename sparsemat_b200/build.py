@@ -1,4 +1,6 @@
-"""Build libsmb200.so in-tree with nvcc for sm_100a:  python -m sparsemat_b200.build"""
+"""Build libsmb200.so in-tree with nvcc for sm_100a (`make -C sparsemat_b200/csrc`).  Rebuild helper for an existing tree:
+importing this module imports the package, which needs the library — a fresh checkout builds through
+`python __graft_entry__.py` (or make) instead."""
 import os
 import subprocess
 import sys
