@@ -82,6 +82,9 @@ extern "C" {
     pub fn smb200_bilinear(a: *mut smb200_crs, lhs: *const smb200_vec, rhs: *const smb200_vec, out: *mut f64) -> smb200_status;
     pub fn smb200_cg_solve(a: *mut smb200_crs, b: *const smb200_vec, x: *mut smb200_vec, tol: f64, relative: i32,
                            iter_max: u64, stats: *mut smb200_cg_stats) -> smb200_status;
+    pub fn smb200_crs_diagonal(a: *const smb200_crs, d: *mut smb200_vec) -> smb200_status;
+    pub fn smb200_pcg_jacobi_solve(a: *mut smb200_crs, b: *const smb200_vec, x: *mut smb200_vec, tol: f64, relative: i32,
+                                   iter_max: u64, stats: *mut smb200_cg_stats) -> smb200_status;
 
     pub fn smb200_par_locate(n_blocks: u64, max_n_rows: u64, row: u64, block: *mut u64, local_row: *mut u64) -> smb200_status;
     pub fn smb200_comm_unique_id(out128: *mut c_void) -> smb200_status;

@@ -4,7 +4,7 @@ The product is ``lib/libsmb200.so`` (hand-written CUDA + the C ABI of ``include/
 package is the thin Python mirror of the reference's interface used by the tests and the bench.
 """
 from .api import (  # noqa: F401
-    ConjugateGradient, Context, DenseVec, DistCRS, Event, Panic, SmbError, SparseMatCRS, SparseMatIndexList,
+    ConjugateGradient, Context, DenseVec, DistCRS, Event, JacobiPCG, Panic, SmbError, SparseMatCRS, SparseMatIndexList,
     SparseMatPar, crs_from_indexlist_arrays, crsfile_read, crsfile_write, ghost_plan, partition_rows, partition_rows_by_nnz, pinned_empty,
 )
 from ._ffi import (  # noqa: F401

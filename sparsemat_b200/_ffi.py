@@ -124,6 +124,8 @@ PROTOTYPES = {
     "smb200_bilinear": (_i32, [_p, _p, _p, _dp]),
     "smb200_cg_solve": (_i32, [_p, _p, _p, C.c_double, _i32, _u64, C.POINTER(CgStats)]),
     "smb200_cg_history": (_i32, [_p, _dp, _u64, _u64p]),
+    "smb200_crs_diagonal": (_i32, [_p, _p]),
+    "smb200_pcg_jacobi_solve": (_i32, [_p, _p, _p, C.c_double, _i32, _u64, C.POINTER(CgStats)]),
     "smb200_par_locate": (_i32, [_u64, _u64, _u64, _u64p, _u64p]),
     "smb200_partition_rows": (_i32, [_u64, C.c_uint32, _u64, _u64p]),
     "smb200_partition_rows_by_nnz": (_i32, [_i32, _u64, _p, C.c_uint32, _u64p]),

@@ -377,6 +377,12 @@ class SparseMatCRS:
         d["variant_name"] = F.VARIANT_NAMES.get(p.variant, "?")
         return d
 
+    def diagonal(self) -> DenseVec:
+        """d[i] = get(i, i) (first stored entry of row i with column i, else 0) as a device vector."""
+        d = DenseVec(self.ctx, self.n_rows(), self.dtype)
+        check(lib.smb200_crs_diagonal(self._h, d._h))
+        return d
+
     def scale(self, s: float):                                         # sparsemat_crs.rs:153-157
         check(lib.smb200_crs_scale(self._h, float(s)))
 
@@ -531,6 +537,25 @@ class ConjugateGradient:
         if n.value:
             check(lib.smb200_cg_history(mat._h, out.ctypes.data_as(C.POINTER(C.c_double)), n.value, C.byref(n)))
         return out
+
+
+class JacobiPCG:
+    """Additive (the reference has no preconditioner): CG preconditioned with the inverse diagonal.  Same constructor,
+    checks and panics as ``ConjugateGradient``.  EXPERIMENTAL in round 1 (first hardware run pending)."""
+
+    def __init__(self, tol: float = 1e-12, iter_max: int = 10_000, relative: bool = False):
+        self.tol, self.iter_max, self.relative = tol, iter_max, relative
+        self.last_stats = None
+
+    def solve(self, mat: SparseMatCRS, b: DenseVec, x: DenseVec) -> None:
+        self.solve_with_stats(mat, b, x)
+
+    def solve_with_stats(self, mat: SparseMatCRS, b: DenseVec, x: DenseVec) -> dict:
+        st = F.CgStats()
+        check(lib.smb200_pcg_jacobi_solve(mat._h, b._h, x._h, self.tol, int(self.relative), self.iter_max, C.byref(st)))
+        self.last_stats = {"iterations": st.iterations, "final_residual": st.final_residual,
+                           "converged": bool(st.converged), "device_ms": st.device_ms, "launches": st.launches}
+        return self.last_stats
 
 
 # ---- partition contract + multi-GPU ---------------------------------------------------------------------------

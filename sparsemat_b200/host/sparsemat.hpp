@@ -279,6 +279,29 @@ private:
     bool relative_ = false;
 };
 
+// Additive (the reference has no preconditioner): CG preconditioned with the inverse diagonal.  Same constructor
+// arguments, checks and panics as ConjugateGradient.  EXPERIMENTAL in round 1 (first hardware run pending).
+class JacobiPCG {
+public:
+    JacobiPCG() = default;
+    JacobiPCG(double tol, uint64_t iter_max, bool relative = false) : tol_(tol), iter_max_(iter_max), relative_(relative) {}
+    template <class T, class I>
+    CgStats solve_with_stats(const SparseMatCRS<T, I>& mat, const DenseVec<T>& b, DenseVec<T>& x) const {
+        smb200_cg_stats st;
+        check(smb200_pcg_jacobi_solve(mat.raw(), b.raw(), x.raw(), tol_, relative_ ? 1 : 0, iter_max_, &st));
+        CgStats out;
+        out.iterations = st.iterations; out.final_residual = st.final_residual; out.converged = st.converged != 0;
+        out.device_ms = st.device_ms;
+        return out;
+    }
+    template <class T, class I>
+    void solve(const SparseMatCRS<T, I>& mat, const DenseVec<T>& b, DenseVec<T>& x) const { solve_with_stats(mat, b, x); }
+private:
+    double tol_ = 1e-12;
+    uint64_t iter_max_ = 10000;
+    bool relative_ = false;
+};
+
 // sparsemat_par.rs:31-35 — the row-block contract the multi-GPU partitioner follows.
 inline std::pair<uint64_t, uint64_t> par_locate(uint64_t n_blocks, uint64_t max_n_rows, uint64_t row) {
     uint64_t b = 0, r = 0;
