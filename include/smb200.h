@@ -251,7 +251,6 @@ smb200_status smb200_cg_solve(smb200_crs* a, const smb200_vec* b, smb200_vec* x,
 /* Optional: copy out up to `cap` residual norms (one per iteration) of the last solve on this matrix. */
 smb200_status smb200_cg_history(const smb200_crs* a, double* out, uint64_t cap, uint64_t* n);
 /* Additive, not in the reference (its LinearSolver trait, linearsolver.rs:6-10, has the unpreconditioned solver only).
- * EXPERIMENTAL in this round (not yet run on hardware).
  * crs_diagonal: d[i] = the first stored entry of row i with column i — what get(i, i) returns (sparsemat_crs.rs:136-143) —
  * or 0.  pcg_jacobi_solve: CG preconditioned with the inverse diagonal; same argument meaning, checks and panics as
  * smb200_cg_solve; ERR_INVALID when a row has no (or a zero) diagonal entry. */

@@ -541,7 +541,7 @@ class ConjugateGradient:
 
 class JacobiPCG:
     """Additive (the reference has no preconditioner): CG preconditioned with the inverse diagonal.  Same constructor,
-    checks and panics as ``ConjugateGradient``.  EXPERIMENTAL in round 1 (first hardware run pending)."""
+    checks and panics as ``ConjugateGradient``."""
 
     def __init__(self, tol: float = 1e-12, iter_max: int = 10_000, relative: bool = False):
         self.tol, self.iter_max, self.relative = tol, iter_max, relative

@@ -9,8 +9,8 @@
 //   loop:  Ap = A p;  alpha = rz / p.Ap;  x += p alpha;  r -= Ap alpha;  stop if sqrt(r.r) < tol
 //          z = D^-1 r;  beta = r.z / rz;  p = p beta + z
 //
-// EXPERIMENTAL in round 1: written after the round's GPU budget was spent; its GPU tests are gated behind
-// SMB200_TEST_UNVALIDATED=1 until the first hardware run.
+// Checked on hardware against the same recurrence in numpy (tests/test_gpu_pcg.py); not yet tuned: a device-scalar,
+// graph-replayed version like cg.cu's is the obvious next step.
 #include "common.cuh"
 #include "reduce.cuh"
 

@@ -280,7 +280,7 @@ private:
 };
 
 // Additive (the reference has no preconditioner): CG preconditioned with the inverse diagonal.  Same constructor
-// arguments, checks and panics as ConjugateGradient.  EXPERIMENTAL in round 1 (first hardware run pending).
+// arguments, checks and panics as ConjugateGradient.
 class JacobiPCG {
 public:
     JacobiPCG() = default;

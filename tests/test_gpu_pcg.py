@@ -1,13 +1,11 @@
-"""GPU tests of code written after round 1's GPU budget was spent (Jacobi-preconditioned CG, smb200_crs_diagonal).
-They have never run on hardware, so they are skipped unless SMB200_TEST_UNVALIDATED=1 — the first thing the next round
-does is run them (`SMB200_TEST_UNVALIDATED=1 python -m pytest tests/test_gpu_unvalidated.py -m gpu`) and drop the gate."""
-import os
-
+"""GPU: the additive solver layer — smb200_crs_diagonal and Jacobi-preconditioned CG.  The reference has
+no preconditioner, so the checker is the same recurrence in f64 numpy/scipy: iteration counts within +-3, the TRUE residual
+||b - A x|| recomputed on the host, fewer iterations than the unpreconditioned solver on a badly scaled SPD matrix, and the
+reference's panics (linearsolver.rs:30-36)."""
 import numpy as np
 import pytest
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("SMB200_TEST_UNVALIDATED") != "1", reason="not yet validated on hardware (opt in with SMB200_TEST_UNVALIDATED=1)")]
+pytestmark = pytest.mark.gpu
 
 
 def _numpy_pcg(a, b, x, tol, iter_max):
