@@ -259,6 +259,8 @@ def run_ours(args):
     ev0, ev1 = ctx.event(), ctx.event()
     launches0 = smb.api.lib.smb200_launch_count()
     with ClockSampler(local) as clk:
+        if multi:
+            a.barrier()                # device-side alignment: every rank's stream starts the timed region together
         ev0.record()
         for _ in range(args.steps):
             step()

@@ -276,7 +276,11 @@ smb200_status smb200_ghost_plan(smb200_itype it, uint64_t nnz, const void* colum
                                 uint32_t rank, const uint64_t* bounds, void* columns_local_out,
                                 uint64_t* ghosts, uint64_t* n_ghosts, uint64_t* ghosts_per_owner);
 
-/* ---- one process per GPU: row-block distributed SpMV / CG over NCCL ------------ */
+/* ---- one process per GPU: row-block distributed SpMV / CG ------------------------
+ * Replaces the reference's unfinished thread-per-block mvp_par (sparsemat_par.rs:37-68): same partition
+ * contract (sparsemat_par.rs:20-35), one rank per GPU instead of one thread per block.  NCCL carries the
+ * set-up only; products and CG scalars move through peer memory over NVLink (CUDA IPC), with NCCL
+ * send/recv + all-reduce as the fallback (SMB200_DIST_P2P=0). */
 /* 128-byte NCCL unique id, created on rank 0 and broadcast by the host (torch.distributed, MPI, ...). */
 smb200_status smb200_comm_unique_id(void* out128);
 smb200_status smb200_comm_init(smb200_ctx* ctx, int32_t rank, int32_t world, const void* uid128);
@@ -295,10 +299,17 @@ smb200_status smb200_dist_dims(const smb200_dist* d, uint64_t* out4);
 smb200_status smb200_dist_local(smb200_dist* d, smb200_crs** out);   /* borrowed local matrix handle */
 /* A vector slice of this rank: dim = n_local_rows, with hidden room for the ghost entries. */
 smb200_status smb200_dist_vec_create(smb200_dist* d, smb200_vec** out);
-/* y_local = (A x)_local: halo/ghost exchange of x over NCCL send/recv overlapped with the interior
- * rows, then the boundary rows. */
+/* y_local = (A x)_local.  Every rank must issue the same sequence of distributed calls.  The ghost
+ * entries of x are stored by the neighbours' kernels into this rank's ghost buffer while the interior
+ * rows are multiplied; the boundary rows follow in the same launch (ring kernel) or right behind. */
 smb200_status smb200_dist_spmv(smb200_dist* d, smb200_vec* x, smb200_vec* y);
 smb200_status smb200_dist_dot(smb200_dist* d, const smb200_vec* x, const smb200_vec* y, double* out);
+/* Stream-ordered barrier over the ranks (no host synchronisation): work queued behind it on the
+ * context stream starts only after every rank's stream has reached its own barrier. */
+smb200_status smb200_dist_barrier(smb200_dist* d);
+/* out4 = {1 if the peer-memory path is active (0: NCCL fallback), halo neighbours of this rank,
+ * distributed products completed, 1 if a peer wait timed out}.  Synchronises the context stream. */
+smb200_status smb200_dist_info(smb200_dist* d, uint64_t* out4);
 smb200_status smb200_dist_cg_solve(smb200_dist* d, const smb200_vec* b, smb200_vec* x, double tol, int32_t relative,
                                    uint64_t iter_max, smb200_cg_stats* stats);
 

@@ -141,6 +141,8 @@ PROTOTYPES = {
     "smb200_dist_vec_create": (_i32, [_p, _pp]),
     "smb200_dist_spmv": (_i32, [_p, _p, _p]),
     "smb200_dist_dot": (_i32, [_p, _p, _p, _dp]),
+    "smb200_dist_barrier": (_i32, [_p]),
+    "smb200_dist_info": (_i32, [_p, _u64p]),
     "smb200_dist_cg_solve": (_i32, [_p, _p, _p, C.c_double, _i32, _u64, C.POINTER(CgStats)]),
     # smb200_host.h
     "smb200_il_create": (_i32, [_i32, _i32, _pp]),

@@ -756,3 +756,12 @@ class DistCRS:
         out = C.c_double()
         check(lib.smb200_dist_dot(self._h, x._h, y._h, C.byref(out)))
         return out.value
+
+    def barrier(self) -> None:
+        """Stream-ordered barrier over the ranks (the host does not wait)."""
+        check(lib.smb200_dist_barrier(self._h))
+
+    def info(self) -> dict:
+        d = (C.c_uint64 * 4)()
+        check(lib.smb200_dist_info(self._h, d))
+        return {"p2p": bool(d[0]), "neighbours": int(d[1]), "products": int(d[2]), "peer_timeout": bool(d[3])}

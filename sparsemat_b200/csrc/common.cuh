@@ -199,6 +199,11 @@ extern thread_local int g_ring_reserve_sms;
 extern thread_local int g_ring_grid_cap;
 // Set while the second and later bands of a band-split product are launched: the stream kernel adds to y instead of writing it.
 extern thread_local bool g_spmv_accumulate;
+// Set by dist.cu around the ONE ring launch of a distributed product: the kernel then also runs the halo protocol of
+// halo.cuh (push the neighbours' ghost entries, wait for this rank's) and walks the row blocks rotated by `rot`.
+struct HaloDev;
+struct HaloLaunch { const HaloDev* dev = nullptr; uint64_t rot = 0; };
+extern thread_local HaloLaunch g_halo;
 // Set while an SpMV reads a caller-owned (smb200_vec_wrap) vector: such memory has no padding behind its last element,
 // so kernels must not round bulk copies of it up to 16 bytes.
 extern thread_local bool g_x_unpadded;
@@ -226,7 +231,7 @@ smb200_status spmv_launch_cg(smb200_crs* m, const SpmvPlan& p, uint64_t row_begi
 smb200_status vec_create_cap(smb200_ctx* ctx, int vt, uint64_t n, uint64_t cap, smb200_vec** out);
 smb200_status gen_laplace_block(smb200_ctx* ctx, int vt, int it, uint64_t nx, uint64_t ny, uint64_t nz, uint64_t row_lo,
                                 uint64_t row_hi, int local_cols, uint64_t n_lo_ghost, uint64_t n_cols_out,
-                                smb200_crs** out);
+                                smb200_crs** out, uint64_t ghost_base = 0);   // ghost_base 0: ghosts right behind the owned columns
 smb200_status cg_prepare(smb200_ctx* ctx, CgWork& w, int vt, uint64_t n, uint64_t p_cap, uint64_t iter_max);
 smb200_status cg_init_launch(smb200_ctx* ctx, CgWork& w, int vt, const void* b, uint64_t n);
 smb200_status cg_xr_launch(smb200_ctx* ctx, CgWork& w, int vt, void* x, uint64_t n);

@@ -10,6 +10,7 @@ thread_local int g_ring_reserve_sms = 0;
 thread_local int g_ring_grid_cap = 0;
 thread_local bool g_spmv_accumulate = false;
 thread_local bool g_x_unpadded = false;
+thread_local HaloLaunch g_halo;
 
 void set_error(const char* fmt, ...) {
     va_list ap;

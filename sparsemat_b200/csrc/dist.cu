@@ -2,14 +2,23 @@
 //
 // Partitioning is SparseMatPar's model (sparsemat_par.rs:20-35): contiguous row blocks, every block
 // needs the slice of x its columns touch.  The reference's sketch replicates x (`Arc<rhs>`,
-// sparsemat_par.rs:39-67); here each rank keeps only [owned | ghosts] and the ghosts are refreshed by a
-// neighbour exchange (NCCL send/recv over NVLink/NVSwitch) on a side stream while the interior rows
-// — those that reference no ghost — are already being multiplied on the main stream.  The two CG dot
-// products are all-reduced as 3+1 doubles per iteration.
+// sparsemat_par.rs:39-67); here each rank keeps only [owned | pad | ghosts] and the ghosts are refreshed per product.
+//
+// Data path (default): PEER MEMORY over NVLink / NVSwitch, no NCCL kernel anywhere in a product or a CG iteration.
+// At creation every rank allocates one "window" (ghost double buffer, flag words, all-reduce slots), the CUDA IPC
+// handles are exchanged once (NCCL all-gather, set-up only) and mapped.  A product is then ONE launch of the ring kernel
+// (spmv.cu): its consumer warps first store the entries the neighbours need straight into the neighbours' ghost buffers
+// and raise their flags; its TMA producer walks the row blocks rotated so that the rows referencing ghosts come last,
+// and spin-waits on this rank's flags only when it reaches them (halo.cuh has the protocol and its hazards argument).
+// Matrices whose local plan is not the ring kernel use the same protocol from two small kernels around the interior
+// launch.  The CG scalars are all-reduced by a 1-CTA kernel that stores every rank's partial into every peer's slot and
+// sums them in rank order (bit-identical on all ranks).
+// Fallback (SMB200_DIST_P2P=0, IPC unavailable, > 16 ranks): NCCL send/recv on a side stream + ncclAllReduce.
 //
 // NCCL is loaded with dlopen at smb200_comm_init time, so single-GPU users carry no NCCL dependency
 // and the library loads on machines without it.
 #include "common.cuh"
+#include "halo.cuh"
 
 #include <dlfcn.h>
 
@@ -85,6 +94,69 @@ __global__ void pack_kernel(const T* __restrict__ x, const uint64_t* __restrict_
     for (uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; k < n; k += stride) out[k] = x[idx[k]];
 }
 
+// ---- peer-memory kernels (protocol: halo.cuh) ------------------------------------------------------------
+// Generic (non-ring) local plans: push | interior launch | wait + land the ghosts behind x's owned part | boundary rows.
+template <class T>
+__global__ void __launch_bounds__(256) halo_push_kernel(const HaloDev* __restrict__ h, const T* __restrict__ x) {
+    const unsigned long long e = __ldcg(h->epoch) + 1ull;
+    halo_push<T>(*h, x, e, blockIdx.x * (uint64_t)blockDim.x + threadIdx.x, (uint64_t)gridDim.x * blockDim.x);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(h->ctr, 1u) == gridDim.x - 1) { h->ctr[0] = 0u; halo_signal(*h, e); }
+    }
+}
+
+template <class T>
+__global__ void __launch_bounds__(256) halo_wait_kernel(const HaloDev* __restrict__ h, T* __restrict__ x) {
+    const unsigned long long e = __ldcg(h->epoch) + 1ull;
+    if (threadIdx.x == 0) halo_wait(*h, e);
+    __syncthreads();
+    const T* gx = (const T*)h->ghost + (e & 1ull) * h->ghost_stride;
+    T* dst = x + h->g0;
+    const uint64_t n = h->n_ghost, stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; k < n; k += stride) dst[k] = __ldcg(gx + k);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(h->ctr + 1, 1u) == gridDim.x - 1) { h->ctr[1] = 0u; *h->epoch = e; }
+    }
+}
+
+// All-reduce (sum) of `count` <= kArSlots doubles: lane q stores this rank's values into rank q's slot array and raises its
+// flag, then waits for rank q's values here.  Thread 0 adds the world's values in rank order, so every rank computes
+// the same bits.  One CTA of 32 threads; epochs alternate between two slot sets (a rank can be one all-reduce ahead).
+__global__ void __launch_bounds__(32) p2p_allreduce_kernel(const ArDev* __restrict__ a, const double* in, double* out, int count,
+                                                           int round_f32) {
+    __shared__ double sv[kMaxPeers][kArSlots];
+    const unsigned long long e = __ldcg(a->epoch) + 1ull;
+    const int world = a->world, me = a->me, q = (int)threadIdx.x;
+    const size_t par = (size_t)(e & 1ull);
+    if (q < world) {
+        double* dst = a->peer_vals[q] + (par * world + me) * kArSlots;
+        for (int k = 0; k < count; ++k) dst[k] = in[k];
+        __threadfence_system();
+        st_release_sys(a->peer_flags[q] + par * world + me, e);
+        const unsigned long long* f = a->flags + par * world + q;
+        const unsigned long long t0 = global_timer_ns();
+        unsigned spins = 0;
+        while (ld_acquire_sys(f) < e) {
+            if ((++spins & 255u) == 0 && global_timer_ns() - t0 > a->timeout_ns) { atomicExch(a->error, 1u); break; }
+        }
+        const double* src = a->vals + (par * world + q) * kArSlots;
+        for (int k = 0; k < count; ++k) sv[q][k] = __ldcg(src + k);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < count; ++k) {
+            double sum = 0.0;
+            for (int r = 0; r < world; ++r) sum += sv[r][k];
+            out[k] = round_f32 ? (double)(float)sum : sum;
+        }
+        *a->epoch = e;
+    }
+}
+
 }  // namespace smb
 
 // Default number of SMs a ring interior leaves free for the exchange: 0 = the halo is awaited first.  Measured on B200
@@ -111,6 +183,19 @@ struct smb200_dist {
     // rows [int_begin, int_end) reference no ghost: multiplied while the exchange is in flight
     uint64_t int_begin = 0, int_end = 0;
     smb::SpmvPlan plan_int, plan_lo, plan_hi;
+    // local column numbering: [0, n_local) owned, [g0, g0 + n_ghost) ghosts, g0 = n_local rounded up to 64 (so that a
+    // bulk copy never straddles the two at an unaligned address)
+    uint64_t g0 = 0;
+    // ---- peer memory (halo.cuh) ----
+    bool p2p = false;
+    void* win = nullptr;                          // this rank's window: flags | all-reduce flags | all-reduce slots | ghost double buffer
+    std::vector<void*> peer_base;                 // the peers' windows mapped here (nullptr: self / not mapped)
+    void* misc = nullptr;                         // local words: halo epoch, all-reduce epoch, arrival counters, error
+    smb::HaloDev* h_dev = nullptr;
+    smb::ArDev* ar_dev = nullptr;
+    double* ar_scratch = nullptr;                 // [2 * kArSlots] operands of barriers / dots
+    uint64_t rot = 0;                             // ring block order: first block without lower-ghost rows
+    int n_nbr = 0;
 };
 
 namespace smb {
@@ -120,7 +205,205 @@ static smb200_status dist_build_plans(smb200_dist* d) {
     SMB_TRY(plan_build_range(m, d->plan_int, m->want_variant, m->want_lanes, m->want_flags, d->int_begin, d->int_end));
     SMB_TRY(plan_build_range(m, d->plan_lo, m->want_variant, m->want_lanes, m->want_flags, 0, d->int_begin));
     SMB_TRY(plan_build_range(m, d->plan_hi, m->want_variant, m->want_lanes, m->want_flags, d->int_end, d->n_local));
-    if (!m->plan.built && m->n_rows) SMB_TRY(plan_build(m));          // whole local block: used when the halo is awaited first
+    if (!m->plan.built && m->n_rows) SMB_TRY(plan_build(m));          // whole local block: the ONE launch of a ring product
+    // ring block order: start at the first block whose rows are all interior or upper-boundary rows; the blocks of the
+    // lower-boundary rows wrap around to the end, next to the upper-boundary ones
+    d->rot = 0;
+    if (m->plan.built && m->plan.variant == SMB200_SPMV_RING && d->int_begin > 0 && m->plan.n_blocks > 1) {
+        const size_t is = isize(m->it);
+        std::vector<unsigned char> rows((m->plan.n_blocks + 1) * is);
+        SMB_CUDA(cudaMemcpyAsync(rows.data(), m->plan.blk_rows, rows.size(), cudaMemcpyDeviceToHost, d->ctx->stream));
+        SMB_CUDA(cudaStreamSynchronize(d->ctx->stream));
+        auto row_of = [&](uint64_t b) { return is == 8 ? ((const uint64_t*)rows.data())[b] : (uint64_t)((const uint32_t*)rows.data())[b]; };
+        uint64_t lo = 0, hi = m->plan.n_blocks;            // smallest b with blk_rows[b] >= int_begin
+        while (lo < hi) { const uint64_t mid = (lo + hi) / 2; if (row_of(mid) < d->int_begin) lo = mid + 1; else hi = mid; }
+        d->rot = lo < m->plan.n_blocks ? lo : 0;
+    }
+    return SMB200_OK;
+}
+
+static bool dist_exchanges(const smb200_dist* d) {
+    return !(d->ctx->world == 1 || (d->n_ghost == 0 && d->total_send == 0));
+}
+
+// ---- peer-memory set-up: collective, called once from smb200_dist_create / smb200_dist_laplace ----------------------
+struct P2pRecord {
+    unsigned char handle[64];                 // cudaIpcMemHandle_t of the rank's window
+    uint64_t want;                            // 1: the rank can take the peer-memory path
+    uint64_t stride;                          // its ghost_stride (elements)
+    uint64_t recv_off[kMaxPeers];             // where rank q's entries start inside its ghost buffer
+    uint64_t recv_count[kMaxPeers];
+};
+static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+
+struct WinLayout { size_t flags, ar_flags, ar_vals, ghost, total; };
+static WinLayout win_layout(int world, uint64_t stride, size_t es) {
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    WinLayout L;
+    L.flags = 0;
+    L.ar_flags = up(L.flags + (size_t)world * 8);
+    L.ar_vals = up(L.ar_flags + 2 * (size_t)world * 8);
+    L.ghost = up(L.ar_vals + 2 * (size_t)world * kArSlots * 8);
+    L.total = up(L.ghost + 2 * (size_t)stride * es) + kPadBytes;
+    return L;
+}
+
+static void dist_p2p_release(smb200_dist* d) {
+    for (void*& pb : d->peer_base) if (pb) { cudaIpcCloseMemHandle(pb); pb = nullptr; }
+    if (d->win) { cudaFree(d->win); d->win = nullptr; }
+    if (d->misc) { cudaFree(d->misc); d->misc = nullptr; }
+    if (d->h_dev) { cudaFree(d->h_dev); d->h_dev = nullptr; }
+    if (d->ar_dev) { cudaFree(d->ar_dev); d->ar_dev = nullptr; }
+    if (d->ar_scratch) { cudaFree(d->ar_scratch); d->ar_scratch = nullptr; }
+    d->p2p = false;
+}
+
+static smb200_status dist_p2p_setup(smb200_dist* d) {
+    smb200_ctx* ctx = d->ctx;
+    const int world = ctx->world, me = ctx->rank;
+    d->p2p = false;
+    if (world == 1) return SMB200_OK;
+    ncclComm_t comm = (ncclComm_t)ctx->comm;
+    const size_t es = vsize(d->vt);
+    const char* env = getenv("SMB200_DIST_P2P");
+    bool want = !(env && env[0] == '0') && world <= kMaxPeers;
+    std::vector<int> nbr;
+    for (int q = 0; q < world; ++q)
+        if (q != me && (d->send_count[q] || d->recv_count[q])) nbr.push_back(q);
+    if ((int)nbr.size() > kMaxNbr) want = false;
+    d->n_nbr = (int)nbr.size();
+    const uint64_t stride = ((d->n_ghost + 63) & ~(uint64_t)63) + 64;
+    const WinLayout L = win_layout(world, stride, es);
+    P2pRecord mine;
+    memset(&mine, 0, sizeof mine);
+    if (want) {
+        if (cudaMalloc(&d->win, L.total) != cudaSuccess || cudaMalloc(&d->misc, 256) != cudaSuccess) { cudaGetLastError(); want = false; }
+    }
+    if (want) {
+        cudaMemsetAsync(d->win, 0, L.total, ctx->stream);
+        cudaMemsetAsync(d->misc, 0, 256, ctx->stream);
+        cudaIpcMemHandle_t hnd;
+        if (cudaIpcGetMemHandle(&hnd, d->win) != cudaSuccess) { cudaGetLastError(); want = false; }
+        else memcpy(mine.handle, &hnd, 64);
+    }
+    mine.want = want ? 1 : 0;
+    mine.stride = stride;
+    for (int q = 0; q < world && q < kMaxPeers; ++q) { mine.recv_off[q] = d->recv_off[q]; mine.recv_count[q] = d->recv_count[q]; }
+    // every rank takes part in the exchanges below whatever it wants: all ranks must end up on the same path
+    unsigned char* d_rec = nullptr;
+    SMB_CUDA(cudaMalloc(&d_rec, (size_t)world * sizeof(P2pRecord)));
+    SMB_CUDA(cudaMemcpyAsync(d_rec + (size_t)me * sizeof(P2pRecord), &mine, sizeof mine, cudaMemcpyHostToDevice, ctx->stream));
+    SMB_NCCL(g_nccl.AllGather(d_rec + (size_t)me * sizeof(P2pRecord), d_rec, sizeof(P2pRecord), kNcclUint8, comm, ctx->stream));
+    std::vector<P2pRecord> recs(world);
+    SMB_CUDA(cudaMemcpyAsync(recs.data(), d_rec, (size_t)world * sizeof(P2pRecord), cudaMemcpyDeviceToHost, ctx->stream));
+    SMB_CUDA(cudaStreamSynchronize(ctx->stream));      // (also: every window is zeroed before any peer can learn its handle)
+    cudaFree(d_rec);
+    bool all = true;
+    for (int q = 0; q < world; ++q) all = all && recs[q].want != 0;
+    double fails = 0.0;
+    if (all) {
+        d->peer_base.assign(world, nullptr);
+        for (int q = 0; q < world; ++q) {
+            if (q == me) continue;
+            cudaIpcMemHandle_t hnd;
+            memcpy(&hnd, recs[q].handle, 64);
+            if (cudaIpcOpenMemHandle(&d->peer_base[q], hnd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaGetLastError();
+                d->peer_base[q] = nullptr;
+                fails += 1.0;
+            }
+        }
+        for (int q : nbr)
+            if (recs[q].recv_count[me] != d->send_count[q]) fails += 1.0;     // the two sides' plans must agree
+    }
+    // agree on the outcome (a rank that could not map a peer takes everyone back to NCCL)
+    double* d_f = nullptr;
+    SMB_CUDA(cudaMalloc(&d_f, sizeof(double)));
+    SMB_CUDA(cudaMemcpyAsync(d_f, &fails, sizeof fails, cudaMemcpyHostToDevice, ctx->stream));
+    SMB_NCCL(g_nccl.AllReduce(d_f, d_f, 1, kNcclFloat64, kNcclSum, comm, ctx->stream));
+    SMB_CUDA(cudaMemcpyAsync(&fails, d_f, sizeof fails, cudaMemcpyDeviceToHost, ctx->stream));
+    SMB_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_f);
+    if (!all || fails != 0.0) { dist_p2p_release(d); return SMB200_OK; }
+
+    const char* tenv = getenv("SMB200_P2P_TIMEOUT_MS");
+    const unsigned long long timeout_ns = (unsigned long long)(tenv ? atof(tenv) : 10000.0) * 1000000ull;
+    unsigned char* misc = (unsigned char*)d->misc;
+    HaloDev h;
+    memset(&h, 0, sizeof h);
+    h.epoch = (unsigned long long*)(misc + 0);
+    h.ctr = (unsigned*)(misc + 16);
+    h.error = (unsigned*)(misc + 24);
+    h.flags = (unsigned long long*)((unsigned char*)d->win + L.flags);
+    h.ghost = (unsigned char*)d->win + L.ghost;
+    h.ghost_stride = stride;
+    h.n_ghost = d->n_ghost;
+    h.g0 = d->g0;
+    h.timeout_ns = timeout_ns;
+    h.send_idx = (const unsigned long long*)d->send_idx;
+    h.total_send = d->total_send;
+    h.n_nbr = (int)nbr.size();
+    for (int i = 0; i < h.n_nbr; ++i) {
+        const int q = nbr[i];
+        const WinLayout Lq = win_layout(world, recs[q].stride, es);
+        unsigned char* base = (unsigned char*)d->peer_base[q];
+        h.nbr_rank[i] = q;
+        h.peer_flag[i] = (unsigned long long*)(base + Lq.flags) + me;
+        h.peer_ghost[i] = base + Lq.ghost + (size_t)recs[q].recv_off[me] * es;
+        h.peer_stride[i] = recs[q].stride;
+        h.send_off[i] = d->send_off[q];
+        h.send_count[i] = d->send_count[q];
+        h.send_first[i] = d->send_first[q];
+        h.send_contig[i] = d->send_contig[q];
+    }
+    ArDev a;
+    memset(&a, 0, sizeof a);
+    a.epoch = (unsigned long long*)(misc + 8);
+    a.error = h.error;
+    a.timeout_ns = timeout_ns;
+    a.world = world;
+    a.me = me;
+    a.flags = (unsigned long long*)((unsigned char*)d->win + L.ar_flags);
+    a.vals = (double*)((unsigned char*)d->win + L.ar_vals);
+    for (int q = 0; q < world; ++q) {
+        unsigned char* base = q == me ? (unsigned char*)d->win : (unsigned char*)d->peer_base[q];
+        a.peer_flags[q] = (unsigned long long*)(base + L.ar_flags);      // the fixed part of the layout is the same on every rank
+        a.peer_vals[q] = (double*)(base + L.ar_vals);
+    }
+    SMB_CUDA(cudaMalloc(&d->h_dev, sizeof h));
+    SMB_CUDA(cudaMalloc(&d->ar_dev, sizeof a));
+    SMB_CUDA(cudaMalloc(&d->ar_scratch, 2 * kArSlots * sizeof(double)));
+    SMB_CUDA(cudaMemcpy(d->h_dev, &h, sizeof h, cudaMemcpyHostToDevice));
+    SMB_CUDA(cudaMemcpy(d->ar_dev, &a, sizeof a, cudaMemcpyHostToDevice));
+    SMB_CUDA(cudaMemset(d->ar_scratch, 0, 2 * kArSlots * sizeof(double)));
+    d->p2p = true;
+    return SMB200_OK;
+}
+
+// Sum `count` doubles over the ranks, in place or out of place, on the context stream.
+static smb200_status dist_allreduce(smb200_dist* d, const double* in, double* out, int count, bool round_f32) {
+    smb200_ctx* ctx = d->ctx;
+    if (ctx->world == 1) {
+        if (in != out) SMB_CUDA(cudaMemcpyAsync(out, in, count * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        return SMB200_OK;
+    }
+    if (d->p2p) {
+        p2p_allreduce_kernel<<<1, 32, 0, ctx->stream>>>(d->ar_dev, in, out, count, round_f32 ? 1 : 0);
+        count_launch();
+        SMB_CUDA(cudaGetLastError());
+        return SMB200_OK;
+    }
+    SMB_NCCL(g_nccl.AllReduce(in, out, count, kNcclFloat64, kNcclSum, (ncclComm_t)ctx->comm, ctx->stream));
+    return SMB200_OK;
+}
+
+// Did a peer wait run into its timeout?  (host-synchronous; called where the host waits for the stream anyway)
+static smb200_status dist_check_peers(smb200_dist* d) {
+    if (!d->p2p) return SMB200_OK;
+    unsigned err = 0;
+    SMB_CUDA(cudaMemcpy(&err, (unsigned char*)d->misc + 24, sizeof err, cudaMemcpyDeviceToHost));
+    SMB_REQUIRE(err == 0, SMB200_ERR_NCCL, "dist: a peer did not reach the same halo / all-reduce epoch within the timeout "
+                "(SMB200_P2P_TIMEOUT_MS); the ranks have diverged or a peer died");
     return SMB200_OK;
 }
 
@@ -129,7 +412,7 @@ static smb200_status dist_build_plans(smb200_dist* d) {
 static smb200_status dist_exchange_begin(smb200_dist* d, void* x) {
     smb200_ctx* ctx = d->ctx;
     const int world = ctx->world, me = ctx->rank;
-    if (world == 1 || (d->n_ghost == 0 && d->total_send == 0)) return SMB200_OK;
+    if (!dist_exchanges(d)) return SMB200_OK;
     const size_t es = vsize(d->vt);
     for (int q = 0; q < world; ++q) {
         if (q == me || d->send_count[q] == 0 || d->send_contig[q]) continue;
@@ -149,7 +432,7 @@ static smb200_status dist_exchange_begin(smb200_dist* d, void* x) {
             SMB_NCCL(g_nccl.Send(src, d->send_count[q], nccl_vtype(d->vt), q, comm, ctx->aux_stream));
         }
         if (d->recv_count[q]) {
-            char* dst = (char*)x + (d->n_local + d->recv_off[q]) * es;
+            char* dst = (char*)x + (d->g0 + d->recv_off[q]) * es;
             SMB_NCCL(g_nccl.Recv(dst, d->recv_count[q], nccl_vtype(d->vt), q, comm, ctx->aux_stream));
         }
     }
@@ -159,7 +442,7 @@ static smb200_status dist_exchange_begin(smb200_dist* d, void* x) {
 
 static smb200_status dist_exchange_end(smb200_dist* d) {
     smb200_ctx* ctx = d->ctx;
-    if (ctx->world == 1 || (d->n_ghost == 0 && d->total_send == 0)) return SMB200_OK;
+    if (!dist_exchanges(d)) return SMB200_OK;
     SMB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_b, 0));
     return SMB200_OK;
 }
@@ -168,7 +451,39 @@ static smb200_status dist_exchange_end(smb200_dist* d) {
 static smb200_status dist_spmv_impl(smb200_dist* d, void* x, void* y, double* S) {
     smb200_crs* m = d->local;
     smb200_ctx* ctx = d->ctx;
-    const bool exchange = !(ctx->world == 1 || (d->n_ghost == 0 && d->total_send == 0));
+    const bool exchange = dist_exchanges(d);
+    if (exchange && d->p2p) {
+        if (m->plan.built && m->plan.variant == SMB200_SPMV_RING) {
+            // ONE launch: push, interior blocks, wait, boundary blocks (spmv_ring_kernel's halo path)
+            g_halo.dev = d->h_dev;
+            g_halo.rot = d->rot;
+            const smb200_status st = S ? spmv_launch_cg(m, m->plan, 0, d->n_local, x, y, x, S, 0, true)
+                                       : spmv_launch_plan(m, m->plan, 0, d->n_local, x, y, nullptr, 0);
+            g_halo = HaloLaunch();
+            return st;
+        }
+        // any other local plan: push | interior rows | wait + land the ghosts behind x's owned part | boundary rows
+        const unsigned gp = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((d->total_send + 255) / 256, (uint64_t)ctx->sm_count * 2));
+        const unsigned gw = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((d->n_ghost + 1023) / 1024, (uint64_t)ctx->sm_count));
+        if (d->vt == SMB200_F64) halo_push_kernel<double><<<gp, 256, 0, ctx->stream>>>(d->h_dev, (const double*)x);
+        else halo_push_kernel<float><<<gp, 256, 0, ctx->stream>>>(d->h_dev, (const float*)x);
+        count_launch();
+        const bool no_int = d->int_end == d->int_begin;
+        if (S) SMB_TRY(spmv_launch_cg(m, d->plan_int, d->int_begin, d->int_end, x, y, x, S, 0, true));
+        else SMB_TRY(spmv_launch_plan(m, d->plan_int, d->int_begin, d->int_end, x, y, nullptr, 0));
+        if (d->vt == SMB200_F64) halo_wait_kernel<double><<<gw, 256, 0, ctx->stream>>>(d->h_dev, (double*)x);
+        else halo_wait_kernel<float><<<gw, 256, 0, ctx->stream>>>(d->h_dev, (float*)x);
+        count_launch();
+        SMB_CUDA(cudaGetLastError());
+        if (S) {
+            SMB_TRY(spmv_launch_cg(m, d->plan_lo, 0, d->int_begin, x, y, x, S, 1, no_int));
+            SMB_TRY(spmv_launch_cg(m, d->plan_hi, d->int_end, d->n_local, x, y, x, S, 2, no_int && d->int_begin == 0));
+        } else {
+            SMB_TRY(spmv_launch_plan(m, d->plan_lo, 0, d->int_begin, x, y, nullptr, 0));
+            SMB_TRY(spmv_launch_plan(m, d->plan_hi, d->int_end, d->n_local, x, y, nullptr, 0));
+        }
+        return SMB200_OK;
+    }
     SMB_TRY(dist_exchange_begin(d, x));
     // Boundary rows: queued on the (high-priority) side stream right behind the halo receive, so they run as soon
     // as the ghosts have landed, in between the waves of the interior kernel, instead of after it.
@@ -364,6 +679,7 @@ smb200_status smb200_dist_free(smb200_dist* d) {
     plan_free(d->plan_int);
     plan_free(d->plan_lo);
     plan_free(d->plan_hi);
+    dist_p2p_release(d);
     if (d->send_idx) cudaFree(d->send_idx);
     if (d->send_buf) cudaFree(d->send_buf);
     if (d->local) smb200_crs_free(d->local);
@@ -398,9 +714,20 @@ smb200_status smb200_dist_create(smb200_ctx* ctx, smb200_vtype vt, smb200_itype 
     if (s != SMB200_OK) { smb200_dist_free(d); return s; }
     d->n_ghost = n_ghost;
     d->recv_count[me] = 0;
-    s = smb200_crs_upload(ctx, vt, it, d->n_local, d->n_local + n_ghost, nnz_local, values, cols_local.data(), offset_rows_local, &d->local);
+    // ghosts start at a multiple of 64 columns: [owned | pad | ghosts]
+    d->g0 = (d->n_local + 63) & ~(uint64_t)63;
+    if (d->g0 != d->n_local) {
+        const uint64_t shift = d->g0 - d->n_local;
+        if (it == SMB200_U64) { uint64_t* c = (uint64_t*)cols_local.data(); for (uint64_t k = 0; k < nnz_local; ++k) if (c[k] >= d->n_local) c[k] += shift; }
+        else {
+            if (d->g0 + n_ghost > 0xFFFFFFFFull) { smb200_dist_free(d); SMB_FAIL(SMB200_ERR_UNSUPPORTED, "dist_create: local block too large for u32 columns"); }
+            uint32_t* c = (uint32_t*)cols_local.data();
+            for (uint64_t k = 0; k < nnz_local; ++k) if (c[k] >= d->n_local) c[k] += (uint32_t)shift;
+        }
+    }
+    s = smb200_crs_upload(ctx, vt, it, d->n_local, d->g0 + n_ghost, nnz_local, values, cols_local.data(), offset_rows_local, &d->local);
     if (s != SMB200_OK) { smb200_dist_free(d); return s; }
-    d->local->x_extra = n_ghost;
+    d->local->x_extra = d->g0 + n_ghost - d->n_local;
     // interior = longest run of rows without ghost references
     {
         uint64_t best_b = 0, best_e = 0, run_b = 0;
@@ -408,7 +735,7 @@ smb200_status smb200_dist_create(smb200_ctx* ctx, smb200_vtype vt, smb200_itype 
         auto col = [&](uint64_t k) { return it == SMB200_U64 ? ((const uint64_t*)cols_local.data())[k] : (uint64_t)((const uint32_t*)cols_local.data())[k]; };
         for (uint64_t r = 0; r < d->n_local; ++r) {
             bool ghost = false;
-            for (uint64_t k = off(r); k < off(r + 1) && !ghost; ++k) ghost = col(k) >= d->n_local;
+            for (uint64_t k = off(r); k < off(r + 1) && !ghost; ++k) ghost = col(k) >= d->g0;
             if (ghost) { if (r - run_b > best_e - best_b) { best_b = run_b; best_e = r; } run_b = r + 1; }
         }
         if (d->n_local - run_b > best_e - best_b) { best_b = run_b; best_e = d->n_local; }
@@ -416,6 +743,7 @@ smb200_status smb200_dist_create(smb200_ctx* ctx, smb200_vtype vt, smb200_itype 
     }
     s = dist_setup_exchange(d, ghosts);
     if (s == SMB200_OK) s = dist_build_plans(d);
+    if (s == SMB200_OK) s = dist_p2p_setup(d);
     if (s != SMB200_OK) { smb200_dist_free(d); return s; }
     *out = d;
     return SMB200_OK;
@@ -440,9 +768,11 @@ smb200_status smb200_dist_laplace(smb200_ctx* ctx, smb200_vtype vt, smb200_itype
     d->n_local = d->bounds[me + 1] - d->bounds[me];
     const uint64_t n_lo = (nz > 1 && me > 0) ? plane : 0, n_hi = (nz > 1 && me + 1 < world) ? plane : 0;
     d->n_ghost = n_lo + n_hi;
-    smb200_status s = gen_laplace_block(ctx, vt, it, nx, ny, nz, d->row_lo, d->row_lo + d->n_local, 1, n_lo, d->n_local + d->n_ghost, &d->local);
+    d->g0 = (d->n_local + 63) & ~(uint64_t)63;
+    if (it != SMB200_U64 && d->g0 + d->n_ghost > 0xFFFFFFFFull) { smb200_dist_free(d); SMB_FAIL(SMB200_ERR_UNSUPPORTED, "dist_laplace: local block too large for u32 columns"); }
+    smb200_status s = gen_laplace_block(ctx, vt, it, nx, ny, nz, d->row_lo, d->row_lo + d->n_local, 1, n_lo, d->g0 + d->n_ghost, &d->local, d->g0);
     if (s != SMB200_OK) { smb200_dist_free(d); return s; }
-    d->local->x_extra = d->n_ghost;
+    d->local->x_extra = d->g0 + d->n_ghost - d->n_local;
     d->recv_count.assign(world, 0);
     d->recv_off.assign(world, 0);
     d->send_count.assign(world, 0);
@@ -455,6 +785,7 @@ smb200_status smb200_dist_laplace(smb200_ctx* ctx, smb200_vtype vt, smb200_itype
     d->int_begin = std::min<uint64_t>(n_lo, d->n_local);
     d->int_end = std::max<uint64_t>(d->int_begin, d->n_local - std::min<uint64_t>(n_hi, d->n_local));
     s = dist_build_plans(d);
+    if (s == SMB200_OK) s = dist_p2p_setup(d);
     if (s != SMB200_OK) { smb200_dist_free(d); return s; }
     *out = d;
     return SMB200_OK;
@@ -474,13 +805,13 @@ smb200_status smb200_dist_local(smb200_dist* d, smb200_crs** out) {
 
 smb200_status smb200_dist_vec_create(smb200_dist* d, smb200_vec** out) {
     SMB_REQUIRE(d && out, SMB200_ERR_INVALID, "dist_vec_create: NULL argument");
-    return vec_create_cap(d->ctx, d->vt, d->n_local, d->n_local + d->n_ghost, out);
+    return vec_create_cap(d->ctx, d->vt, d->n_local, d->g0 + d->n_ghost, out);
 }
 
 smb200_status smb200_dist_spmv(smb200_dist* d, smb200_vec* x, smb200_vec* y) {
     SMB_REQUIRE(d && x && y, SMB200_ERR_INVALID, "dist_spmv: NULL argument");
     SMB_REQUIRE(x->vt == d->vt && y->vt == d->vt, SMB200_ERR_INVALID, "dist_spmv: value types differ");
-    SMB_REQUIRE(x->n >= d->n_local && x->cap >= d->n_local + d->n_ghost, SMB200_ERR_DIM,
+    SMB_REQUIRE(x->n >= d->n_local && x->cap >= d->g0 + d->n_ghost, SMB200_ERR_DIM,
                 "Dimension mismatch: x must come from smb200_dist_vec_create (room for %llu ghosts)", (unsigned long long)d->n_ghost);
     SMB_REQUIRE(y->n >= d->n_local, SMB200_ERR_DIM, "Dimension mismatch");
     SMB_REQUIRE(x->d != y->d, SMB200_ERR_INVALID, "dist_spmv: x and y alias");
@@ -493,10 +824,37 @@ smb200_status smb200_dist_dot(smb200_dist* d, const smb200_vec* x, const smb200_
     smb200_ctx* ctx = d->ctx;
     const uint64_t n = std::min(x->n, y->n);
     SMB_TRY(dot_launch(ctx, d->vt, x->d, y->d, n, 2));
-    if (ctx->world > 1)
-        SMB_NCCL(g_nccl.AllReduce(ctx->red_result + 2, ctx->red_result + 2, 1, kNcclFloat64, kNcclSum, (ncclComm_t)ctx->comm, ctx->stream));
+    SMB_TRY(dist_allreduce(d, ctx->red_result + 2, ctx->red_result + 2, 1, d->vt == SMB200_F32));
     SMB_TRY(fetch_result(ctx, 2, out));
     if (d->vt == SMB200_F32) *out = (double)(float)*out;
+    return dist_check_peers(d);
+}
+
+smb200_status smb200_dist_barrier(smb200_dist* d) {
+    SMB_REQUIRE(d, SMB200_ERR_INVALID, "dist_barrier: NULL argument");
+    smb200_ctx* ctx = d->ctx;
+    if (ctx->world == 1) return SMB200_OK;
+    if (d->p2p) return dist_allreduce(d, d->ar_scratch, d->ar_scratch + kArSlots, 1, false);
+    SMB_TRY(ensure_reduction_scratch(ctx, 16));
+    SMB_NCCL(g_nccl.AllReduce(ctx->red_partials, ctx->red_partials + 8, 1, kNcclFloat64, kNcclSum, (ncclComm_t)ctx->comm, ctx->stream));
+    return SMB200_OK;
+}
+
+smb200_status smb200_dist_info(smb200_dist* d, uint64_t* out4) {
+    SMB_REQUIRE(d && out4, SMB200_ERR_INVALID, "dist_info: NULL argument");
+    out4[0] = d->p2p ? 1 : 0;
+    out4[1] = (uint64_t)d->n_nbr;
+    out4[2] = 0;
+    out4[3] = 0;
+    if (d->p2p) {
+        SMB_CUDA(cudaStreamSynchronize(d->ctx->stream));
+        unsigned long long ep = 0;
+        unsigned err = 0;
+        SMB_CUDA(cudaMemcpy(&ep, d->misc, sizeof ep, cudaMemcpyDeviceToHost));
+        SMB_CUDA(cudaMemcpy(&err, (unsigned char*)d->misc + 24, sizeof err, cudaMemcpyDeviceToHost));
+        out4[2] = ep;
+        out4[3] = err;
+    }
     return SMB200_OK;
 }
 
@@ -505,17 +863,17 @@ smb200_status smb200_dist_cg_solve(smb200_dist* d, const smb200_vec* b, smb200_v
     SMB_REQUIRE(d && b && x, SMB200_ERR_INVALID, "dist_cg_solve: NULL argument");
     SMB_REQUIRE(b->vt == d->vt && x->vt == d->vt, SMB200_ERR_INVALID, "dist_cg_solve: value types differ");
     SMB_REQUIRE(d->n_local == b->n && d->n_local == x->n, SMB200_ERR_SIZE_MISMATCH, "Matrix and vector size mismatch");
-    SMB_REQUIRE(x->cap >= d->n_local + d->n_ghost, SMB200_ERR_DIM, "Dimension mismatch: x must come from smb200_dist_vec_create");
+    SMB_REQUIRE(x->cap >= d->g0 + d->n_ghost, SMB200_ERR_DIM, "Dimension mismatch: x must come from smb200_dist_vec_create");
     smb200_ctx* ctx = d->ctx;
     smb200_crs* a = d->local;
     CgWork& w = a->cg;
     const uint64_t n = d->n_local;
     const uint64_t launches0 = g_launches;
     const bool multi = ctx->world > 1;
-    ncclComm_t comm = (ncclComm_t)ctx->comm;
+    const bool f32 = d->vt == SMB200_F32;
     if (stats) memset(stats, 0, sizeof *stats);
     SMB_CUDA(cudaSetDevice(ctx->device));
-    SMB_TRY(cg_prepare(ctx, w, d->vt, n, n + d->n_ghost, iter_max));
+    SMB_TRY(cg_prepare(ctx, w, d->vt, n, d->g0 + d->n_ghost, iter_max));
     double* S = w.scalars;
     enum { S_RR = 0, S_PAP = 1, S_RR_NEW = 4, S_THRESH = 5, S_ITER = 6, S_DONE = 7, S_RR_LOCAL = 8, S_COUNT = 16 };   // cg.cu
 
@@ -525,9 +883,16 @@ smb200_status smb200_dist_cg_solve(smb200_dist* d, const smb200_vec* b, smb200_v
         SMB_TRY(smb200_dist_dot(d, b, b, &bb));
         threshold = tol * sqrt(bb);
     }
-    cudaEvent_t ev0, ev1;
-    SMB_CUDA(cudaEventCreate(&ev0));
-    SMB_CUDA(cudaEventCreate(&ev1));
+    struct Events {                       // destroyed on every return path
+        cudaEvent_t ev0 = nullptr, ev1 = nullptr, poll[2] = {nullptr, nullptr};
+        ~Events() { for (cudaEvent_t e : {ev0, ev1, poll[0], poll[1]}) if (e) cudaEventDestroy(e); }
+    } evs;
+    SMB_CUDA(cudaEventCreate(&evs.ev0));
+    SMB_CUDA(cudaEventCreate(&evs.ev1));
+    SMB_CUDA(cudaEventCreateWithFlags(&evs.poll[0], cudaEventDisableTiming));
+    SMB_CUDA(cudaEventCreateWithFlags(&evs.poll[1], cudaEventDisableTiming));
+    cudaEvent_t ev0 = evs.ev0, ev1 = evs.ev1;
+    cudaEvent_t* poll_ev = evs.poll;
     SMB_CUDA(cudaEventRecord(ev0, ctx->stream));
     double init[S_COUNT] = {0};
     init[S_THRESH] = threshold;
@@ -536,16 +901,13 @@ smb200_status smb200_dist_cg_solve(smb200_dist* d, const smb200_vec* b, smb200_v
     // r = b - A x ; p = r ; rr = r.r
     SMB_TRY(dist_spmv_impl(d, x->d, w.ap, nullptr));
     SMB_TRY(cg_init_launch(ctx, w, d->vt, b->d, n));
-    if (multi) SMB_NCCL(g_nccl.AllReduce(S + S_RR_LOCAL, S + S_RR_NEW, 1, kNcclFloat64, kNcclSum, comm, ctx->stream));
+    if (multi) SMB_TRY(dist_allreduce(d, S + S_RR_LOCAL, S + S_RR_NEW, 1, f32));
 
     const char* benv = getenv("SMB200_CG_BATCH");
     int batch = benv ? atoi(benv) : 8;
     if (batch < 1) batch = 1;
     const char* genv = getenv("SMB200_CG_GRAPH");
     const bool use_graph = !(genv && genv[0] == '0');
-    cudaEvent_t poll_ev[2];
-    SMB_CUDA(cudaEventCreateWithFlags(&poll_ev[0], cudaEventDisableTiming));
-    SMB_CUDA(cudaEventCreateWithFlags(&poll_ev[1], cudaEventDisableTiming));
     smb200_status st = SMB200_OK;
     uint64_t launched = 0, rounds = 0;
     bool finished = false;
@@ -555,9 +917,9 @@ smb200_status smb200_dist_cg_solve(smb200_dist* d, const smb200_vec* b, smb200_v
     auto iteration = [&]() -> smb200_status {
         if (multi && cudaMemsetAsync(S + S_PAP, 0, 3 * sizeof(double), ctx->stream) != cudaSuccess) { set_error("dist_cg_solve: memset failed"); return SMB200_ERR_CUDA; }
         SMB_TRY(dist_spmv_impl(d, w.p, w.ap, S));
-        if (multi && g_nccl.AllReduce(S + S_PAP, S + S_PAP, 3, kNcclFloat64, kNcclSum, comm, ctx->stream) != 0) { set_error("dist_cg_solve: all-reduce failed"); return SMB200_ERR_NCCL; }
+        if (multi) SMB_TRY(dist_allreduce(d, S + S_PAP, S + S_PAP, 3, false));
         SMB_TRY(cg_xr_launch(ctx, w, d->vt, x->d, n));
-        if (multi && g_nccl.AllReduce(S + S_RR_LOCAL, S + S_RR_NEW, 1, kNcclFloat64, kNcclSum, comm, ctx->stream) != 0) { set_error("dist_cg_solve: all-reduce failed"); return SMB200_ERR_NCCL; }
+        if (multi) SMB_TRY(dist_allreduce(d, S + S_RR_LOCAL, S + S_RR_NEW, 1, f32));     // r.r is a T in the reference: rounded like the single-GPU path
         return cg_p_launch(ctx, w, d->vt, n);
     };
     // the first iteration runs eagerly: it performs every lazy allocation / connection set-up outside of stream capture
@@ -604,17 +966,22 @@ smb200_status smb200_dist_cg_solve(smb200_dist* d, const smb200_vec* b, smb200_v
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) { set_error("dist_cg_solve: %s", cudaGetErrorString(e)); st = SMB200_ERR_CUDA; }
     }
-    if (st == SMB200_OK && stats) {
+    if (st == SMB200_OK) {
         const double* H = w.scalars_host;
-        stats->iterations = (uint64_t)H[S_ITER];
-        stats->final_residual = sqrt(H[S_RR_NEW]);
-        stats->converged = H[S_DONE] != 0.0;
-        cudaEventElapsedTime(&stats->device_ms, ev0, ev1);
-        stats->launches = g_launches - launches0;
+        const uint64_t iters = (uint64_t)H[S_ITER];
+        w.history_host.assign(iters < w.hist_cap ? iters : w.hist_cap, 0.0);      // smb200_cg_history(smb200_dist_local(d)) reads it
+        if (!w.history_host.empty())
+            cudaMemcpy(w.history_host.data(), w.history, w.history_host.size() * sizeof(double), cudaMemcpyDeviceToHost);
+        if (stats) {
+            stats->iterations = iters;
+            stats->final_residual = sqrt(H[S_RR_NEW]);
+            stats->converged = H[S_DONE] != 0.0;
+            cudaEventElapsedTime(&stats->device_ms, ev0, ev1);
+            stats->launches = g_launches - launches0;
+        }
+        st = dist_check_peers(d);
     }
     if (st != SMB200_OK) cudaStreamSynchronize(ctx->stream);
-    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
-    cudaEventDestroy(poll_ev[0]); cudaEventDestroy(poll_ev[1]);
     return st;
 }
 

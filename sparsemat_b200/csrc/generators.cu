@@ -9,17 +9,17 @@ namespace smb {
 struct LaplaceGeom {
     uint64_t nx, ny, nz, plane;
     uint64_t row_lo, row_hi;
-    // column numbering: global, or local = [owned | ghost plane below | ghost plane above]
+    // column numbering: global, or local = [owned | pad | ghost plane below | ghost plane above], ghosts from ghost_base on
     int local_cols;
     uint64_t n_lo_ghost;
+    uint64_t ghost_base;
 };
 
 __device__ __forceinline__ uint64_t laplace_col(const LaplaceGeom& g, uint64_t c) {
     if (!g.local_cols) return c;
-    const uint64_t n_local = g.row_hi - g.row_lo;
     if (c >= g.row_lo && c < g.row_hi) return c - g.row_lo;
-    if (c < g.row_lo) return n_local + (c - (g.row_lo - g.n_lo_ghost));
-    return n_local + g.n_lo_ghost + (c - g.row_hi);
+    if (c < g.row_lo) return g.ghost_base + (c - (g.row_lo - g.n_lo_ghost));
+    return g.ghost_base + g.n_lo_ghost + (c - g.row_hi);
 }
 
 template <class I>
@@ -77,7 +77,7 @@ static uint64_t laplace_nnz_rows(uint64_t nx, uint64_t ny, uint64_t nz, uint64_t
 // Shared by smb200_gen_laplace and the distributed z-slab builder (dist.cu).
 smb200_status gen_laplace_block(smb200_ctx* ctx, int vt, int it, uint64_t nx, uint64_t ny, uint64_t nz, uint64_t row_lo,
                                 uint64_t row_hi, int local_cols, uint64_t n_lo_ghost, uint64_t n_cols_out,
-                                smb200_crs** out) {
+                                smb200_crs** out, uint64_t ghost_base) {
     SMB_REQUIRE(nx && ny && nz, SMB200_ERR_INVALID, "gen_laplace: empty grid");
     const uint64_t N = nx * ny * nz;
     SMB_REQUIRE(row_lo <= row_hi && row_hi <= N, SMB200_ERR_INVALID, "gen_laplace: bad row range");
@@ -86,7 +86,7 @@ smb200_status gen_laplace_block(smb200_ctx* ctx, int vt, int it, uint64_t nx, ui
     smb200_crs* m = nullptr;
     SMB_TRY(crs_alloc(ctx, vt, it, n, n_cols_out, nnz, &m));
     if (n == 0) { *out = m; return SMB200_OK; }
-    LaplaceGeom g{nx, ny, nz, nx * ny, row_lo, row_hi, local_cols, n_lo_ghost};
+    LaplaceGeom g{nx, ny, nz, nx * ny, row_lo, row_hi, local_cols, n_lo_ghost, ghost_base ? ghost_base : row_hi - row_lo};
     const unsigned grid = (unsigned)((n + 1 + 255) / 256);
     if (it == SMB200_U64) laplace_len_kernel<uint64_t><<<grid, 256, 0, ctx->stream>>>(g, (uint64_t*)m->offsets);
     else laplace_len_kernel<uint32_t><<<grid, 256, 0, ctx->stream>>>(g, (uint32_t*)m->offsets);

@@ -1,0 +1,114 @@
+// Peer-memory plumbing of the row-block distributed path (dist.cu): ghost entries of x and the CG scalars travel by
+// plain stores into the neighbour's HBM over NVLink / NVSwitch (CUDA IPC mappings exchanged once, when the distributed
+// matrix is created) instead of NCCL send/recv and all-reduce kernels.
+//
+// Halo protocol, one "epoch" per distributed product (SparseMatPar's model, sparsemat_par.rs:39-67: every row block needs
+// the entries of x its columns touch; here only those entries move):
+//   1. x is final when the product's first kernel starts (stream order).  Its threads copy the entries the neighbours need
+//      into the neighbours' ghost buffers (half `epoch & 1` of a double buffer), fence, and the last CTA to finish its share
+//      stores the epoch number into every neighbour's flag word (release, system scope).
+//   2. Whoever needs ghost entries — the TMA producer of a block with a ghost window, or the wait kernel in front of the
+//      boundary rows — spins (acquire, system scope) until all neighbours' flags have reached the epoch.
+//   3. A product ends only after all neighbours' flags of its epoch were seen, so a rank can be at most one epoch ahead of
+//      a neighbour: the half it writes next is never the half that neighbour may still be reading.
+// No kernel of another rank has to be resident for a store to land, so nothing here can dead-lock on SM occupancy; waits
+// are bounded by `timeout_ns` (a lost peer sets the error word instead of hanging the GPU).
+#pragma once
+#include <cstdint>
+
+namespace smb {
+
+constexpr int kMaxNbr = 8;       // neighbours in the halo exchange of one rank
+constexpr int kMaxPeers = 16;    // ranks of a peer-memory communicator (one NVSwitch domain)
+constexpr int kArSlots = 4;      // doubles per all-reduce
+
+struct HaloDev {
+    unsigned long long* epoch;            // [1] last completed epoch (local)
+    unsigned* ctr;                        // [2] arrivals: push finished / product finished; zero between launches (local)
+    unsigned long long* flags;            // [world] flags[q] = last epoch rank q has pushed into this rank's buffer (peers write)
+    unsigned* error;                      // [1] set when a wait ran into the timeout
+    void* ghost;                          // this rank's ghost buffer: 2 halves of ghost_stride elements (peers write)
+    unsigned long long ghost_stride;      // elements per half
+    unsigned long long n_ghost;
+    unsigned long long g0;                // first ghost column in local numbering (a multiple of 64)
+    unsigned long long timeout_ns;
+    const unsigned long long* send_idx;   // local row ids to pack, grouped by neighbour
+    unsigned long long total_send;
+    int n_nbr;
+    int nbr_rank[kMaxNbr];
+    unsigned long long* peer_flag[kMaxNbr];     // &flags[me] inside neighbour i's window
+    void* peer_ghost[kMaxNbr];                  // neighbour i's ghost buffer at this rank's receive offset
+    unsigned long long peer_stride[kMaxNbr];    // neighbour i's ghost_stride
+    unsigned long long send_off[kMaxNbr], send_count[kMaxNbr], send_first[kMaxNbr];
+    int send_contig[kMaxNbr];
+};
+
+struct ArDev {
+    unsigned long long* epoch;            // [1] local
+    unsigned long long* flags;            // [2][world] (peers write)
+    double* vals;                         // [2][world][kArSlots] (peers write)
+    unsigned* error;
+    unsigned long long timeout_ns;
+    int world, me;
+    unsigned long long* peer_flags[kMaxPeers];
+    double* peer_vals[kMaxPeers];
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+
+// Step 1, data: thread `tid` of `nthreads` copies its share of the entries the neighbours need.
+template <class T>
+__device__ __forceinline__ void halo_push(const HaloDev& h, const T* __restrict__ x, unsigned long long e, uint64_t tid, uint64_t nthreads) {
+    const int n = h.n_nbr;
+    for (int i = 0; i < n; ++i) {
+        const unsigned long long cnt = h.send_count[i];
+        if (cnt == 0) continue;
+        T* dst = (T*)h.peer_ghost[i] + (e & 1ull) * h.peer_stride[i];
+        if (h.send_contig[i]) {
+            const T* src = x + h.send_first[i];
+            for (unsigned long long k = tid; k < cnt; k += nthreads) dst[k] = src[k];
+        } else {
+            const unsigned long long* idx = h.send_idx + h.send_off[i];
+            for (unsigned long long k = tid; k < cnt; k += nthreads) dst[k] = x[idx[k]];
+        }
+    }
+    __threadfence_system();
+}
+
+// Step 1, flags: one thread, after every pushing thread of the grid has fenced and arrived.
+__device__ __forceinline__ void halo_signal(const HaloDev& h, unsigned long long e) {
+    __threadfence_system();
+    for (int i = 0; i < h.n_nbr; ++i) st_release_sys(h.peer_flag[i], e);
+}
+
+// Step 2: one thread.  Returns false after a timeout (the error word is set; the caller carries on with stale ghosts so
+// that the kernel terminates and the host can report the failure).
+__device__ __forceinline__ bool halo_wait(const HaloDev& h, unsigned long long e) {
+    const unsigned long long t0 = global_timer_ns();
+    for (int i = 0; i < h.n_nbr; ++i) {
+        const unsigned long long* f = h.flags + h.nbr_rank[i];
+        unsigned spins = 0;
+        while (ld_acquire_sys(f) < e) {
+            if ((++spins & 255u) == 0 && global_timer_ns() - t0 > h.timeout_ns) { atomicExch(h.error, 1u); return false; }
+            __nanosleep(40);
+        }
+    }
+    return true;
+}
+#endif
+
+}  // namespace smb

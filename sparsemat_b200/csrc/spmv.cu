@@ -24,6 +24,7 @@
 //          SMB200_FLAG_L2_PERSIST_X    L2 access-policy window over x for everything else.
 // Every variant can fuse a dot product  sum_r w[r]*y[r]  into its epilogue (K7a, used by CG).
 #include "common.cuh"
+#include "halo.cuh"
 #include "reduce.cuh"
 
 #include <cstdlib>
@@ -745,7 +746,7 @@ __device__ __forceinline__ void ring_row_span(const I* so, uint64_t r, uint64_t 
 template <class T, class I, bool DOT, int NSEG, bool O16 = false>
 __device__ __forceinline__ double ring_rows(const T* sv, const I* sc, const I* so, const T* sx, const RingDesc& d,
                                             unsigned lane_id, unsigned n_lanes, const T* __restrict__ x, T* __restrict__ y,
-                                            const T* __restrict__ w) {
+                                            const T* __restrict__ w, const T* gx = nullptr, unsigned long long g0 = ~0ull) {
     const uint64_t r0 = d.r0, r1 = d.r1, a0 = d.a0, r0a = d.r0a;
     RingWin<T, I, NSEG> win;
     win.lo1 = (I)d.lo[1]; win.lo2 = (I)d.lo[2]; win.lo3 = (I)d.lo[3];
@@ -762,7 +763,7 @@ __device__ __forceinline__ double ring_rows(const T* sv, const I* sc, const I* s
             const I c = sc[k];
             T xv;
             if constexpr (NSEG > 0) xv = sx[win.at(c)];
-            else xv = __ldg(x + (size_t)c);
+            else xv = (unsigned long long)c >= g0 ? __ldcg(gx + ((unsigned long long)c - g0)) : __ldg(x + (size_t)c);   // ghosts: written by peers during this launch
             sum = add_rn(sum, mul_rn(xv, sv[k]));
         }
         y[r] = sum;
@@ -800,7 +801,7 @@ spmv_ring_kernel(const T* __restrict__ vals, const I* __restrict__ cols, const I
                  const unsigned* __restrict__ seg_len, unsigned n_blocks, unsigned cap, unsigned ocap, unsigned xcap,
                  unsigned colb, unsigned stages, int xwin_ok, const uint16_t* __restrict__ lcols, unsigned long long lcols_base,
                  const uint16_t* __restrict__ loffs, unsigned long long row_begin, const T* __restrict__ x, T* __restrict__ y,
-                 DotArgs dot) {
+                 DotArgs dot, const HaloDev* __restrict__ halo, unsigned rot) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full[kPipeMaxStages];    // producer -> consumers: the stage's bytes have landed
     __shared__ __align__(8) uint64_t empty[kPipeMaxStages];   // consumers -> producer: every consumer warp has left the stage
@@ -818,6 +819,17 @@ spmv_ring_kernel(const T* __restrict__ vals, const I* __restrict__ cols, const I
     const unsigned n_my = blockIdx.x < n_blocks ? (n_blocks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     if (tid == 0)
         for (unsigned s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kConsumerWarps); }
+    // Distributed product (dist.cu, halo.cuh): this launch is epoch `epoch` of the halo protocol.  The ghost entries of x
+    // live in half `epoch & 1` of the rank's ghost buffer, written by the neighbours' launches of the same epoch.
+    const bool dist = halo != nullptr;
+    unsigned long long epoch = 0, g0 = ~0ull;
+    const T* gx = nullptr;
+    if (dist) {
+        epoch = __ldcg(halo->epoch) + 1ull;
+        g0 = halo->g0;
+        gx = (const T*)halo->ghost + (epoch & 1ull) * halo->ghost_stride;
+    }
+    bool waited = false;                     // producer lane: the neighbours' flags of this epoch have been seen
     __syncthreads();
     double acc = 0.0;
 
@@ -826,7 +838,10 @@ spmv_ring_kernel(const T* __restrict__ vals, const I* __restrict__ cols, const I
         if (tid == 0) {
             unsigned s = 0, parity = 0;
             for (unsigned j = 0; j < n_my; ++j) {
-                const size_t b = (size_t)blockIdx.x + (size_t)j * gridDim.x;
+                // `rot` rotates the block order so that the rows that need ghost entries come last (their wait is then over
+                // before it starts)
+                size_t b = (size_t)blockIdx.x + (size_t)j * gridDim.x + rot;
+                if (b >= n_blocks) b -= n_blocks;
                 const unsigned long long r0 = (unsigned long long)__ldg(blk_rows + b), r1 = (unsigned long long)__ldg(blk_rows + b + 1);
                 const unsigned long long n0 = (unsigned long long)__ldg(blk_nnz + b), n1 = (unsigned long long)__ldg(blk_nnz + b + 1);
                 unsigned long long lo[kNSeg];
@@ -860,6 +875,13 @@ spmv_ring_kernel(const T* __restrict__ vals, const I* __restrict__ cols, const I
                 const unsigned cbytes = count * (c16 ? 2u : (unsigned)sizeof(I));
                 unsigned bytes = count * (unsigned)sizeof(T) + cbytes + obytes;
                 if (xw) bytes += xtotal * (unsigned)sizeof(T);
+                if (dist && !waited) {
+                    // a block without windows gathers any column; a windowed one needs the ghosts if a window reaches past g0
+                    bool need = !xw;
+#pragma unroll
+                    for (int i = 0; i < kNSeg; ++i) need = need || (len[i] != 0u && lo[i] + len[i] > g0);
+                    if (need) { halo_wait(*halo, epoch); fence_proxy_async_global(); waited = true; }
+                }
                 mbar_expect_tx(&full[s], bytes);
                 if (count) {
                     bulk_g2s(base, vals + a0, count * (unsigned)sizeof(T), &full[s]);
@@ -872,14 +894,38 @@ spmv_ring_kernel(const T* __restrict__ vals, const I* __restrict__ cols, const I
                     unsigned at = 0;
 #pragma unroll
                     for (int i = 0; i < kNSeg; ++i)
-                        if (len[i]) { bulk_g2s(base + o_x + (size_t)at * sizeof(T), x + lo[i], len[i] * (unsigned)sizeof(T), &full[s]); at += len[i]; }
+                        if (len[i]) {
+                            unsigned char* dstw = base + o_x + (size_t)at * sizeof(T);
+                            if (lo[i] + len[i] <= g0) {                    // owned entries (always, when not distributed)
+                                bulk_g2s(dstw, x + lo[i], len[i] * (unsigned)sizeof(T), &full[s]);
+                            } else if (lo[i] >= g0) {                      // ghost entries: this epoch's half of the ghost buffer
+                                bulk_g2s(dstw, gx + (lo[i] - g0), len[i] * (unsigned)sizeof(T), &full[s]);
+                            } else {                                       // a window across the end of the owned part (g0 is 16-byte aligned)
+                                const unsigned n1 = (unsigned)(g0 - lo[i]);
+                                bulk_g2s(dstw, x + lo[i], n1 * (unsigned)sizeof(T), &full[s]);
+                                bulk_g2s(dstw + (size_t)n1 * sizeof(T), gx, (len[i] - n1) * (unsigned)sizeof(T), &full[s]);
+                            }
+                            at += len[i];
+                        }
                 }
                 if (++s == stages) { s = 0; parity ^= 1u; }
             }
+            // a product ends only after every neighbour's flag of its epoch was seen (halo.cuh, step 3)
+            if (dist && blockIdx.x == 0 && !waited) halo_wait(*halo, epoch);
         }
     } else {
         // ---- consumer warps: no block-wide barrier; a warp releases the stage as soon as its own rows are done ------------
         const unsigned lane_id = tid - 32, n_lanes = kRingThreads - 32;
+        if (dist) {
+            // x is final (stream order): while the first stages are still in flight, put the entries the neighbours need into
+            // their ghost buffers; the CTA whose consumers finish last raises the neighbours' flags
+            halo_push<T>(*halo, x, epoch, (uint64_t)blockIdx.x * n_lanes + lane_id, (uint64_t)gridDim.x * n_lanes);
+            asm volatile("bar.sync 1, %0;" ::"r"(n_lanes) : "memory");
+            if (lane_id == 0) {
+                __threadfence();
+                if (atomicAdd(halo->ctr, 1u) == gridDim.x - 1) halo_signal(*halo, epoch);
+            }
+        }
         unsigned s = 0, parity = 0;
         for (unsigned i = 0; i < n_my; ++i) {
             mbar_wait(&full[s], parity);
@@ -896,8 +942,8 @@ spmv_ring_kernel(const T* __restrict__ vals, const I* __restrict__ cols, const I
                 else acc += ring_rows_c16<T, I, DOT, false>(sv, sc16, so, sx, d, lane_id, n_lanes, y, w);
             } else switch (d.xwin) {              // number of x windows of the block (block-uniform)
                 case 0:
-                    if (d.o16) acc += ring_rows<T, I, DOT, 0, true>(sv, sc, so, sx, d, lane_id, n_lanes, x, y, w);
-                    else acc += ring_rows<T, I, DOT, 0, false>(sv, sc, so, sx, d, lane_id, n_lanes, x, y, w);
+                    if (d.o16) acc += ring_rows<T, I, DOT, 0, true>(sv, sc, so, sx, d, lane_id, n_lanes, x, y, w, gx, g0);
+                    else acc += ring_rows<T, I, DOT, 0, false>(sv, sc, so, sx, d, lane_id, n_lanes, x, y, w, gx, g0);
                     break;
                 case 1: acc += ring_rows<T, I, DOT, 1>(sv, sc, so, sx, d, lane_id, n_lanes, x, y, w); break;
                 case 2: acc += ring_rows<T, I, DOT, 2>(sv, sc, so, sx, d, lane_id, n_lanes, x, y, w); break;
@@ -907,6 +953,18 @@ spmv_ring_kernel(const T* __restrict__ vals, const I* __restrict__ cols, const I
             __syncwarp();
             if ((tid & 31) == 0) mbar_arrive(&empty[s]);
             if (++s == stages) { s = 0; parity ^= 1u; }
+        }
+    }
+    if (dist) {
+        // the CTA that finishes last closes the epoch and re-arms the arrival counters for the next launch
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            if (atomicAdd(halo->ctr + 1, 1u) == gridDim.x - 1) {
+                halo->ctr[0] = 0u;
+                halo->ctr[1] = 0u;
+                *halo->epoch = epoch;
+            }
         }
     }
     if constexpr (DOT) finish_dot<T, kRingThreads>(acc, dot);
@@ -1562,7 +1620,8 @@ static smb200_status launch_typed(smb200_crs* m, const SpmvPlan& p, uint64_t rb,
             kern<<<(unsigned)grid, kRingThreads, smem, st>>>(vals, cols, offs, (const I*)p.blk_rows, (const I*)p.blk_nnz, p.seg_lo, p.seg_len,
                                                            (unsigned)p.n_blocks, sh.cap, p.ocap, xcap, colb, (unsigned)stages, xwin_ok,
                                                            xwin_ok ? p.lcols : nullptr, (unsigned long long)p.lcols_base, p.loffs,
-                                                           (unsigned long long)p.loffs_row_begin, xx, yy, dot);
+                                                           (unsigned long long)p.loffs_row_begin, xx, yy, dot, g_halo.dev,
+                                                           g_halo.dev ? (unsigned)(g_halo.rot % p.n_blocks) : 0u);
         } else if (p.variant == SMB200_SPMV_STREAM_PIPE) {
             int stages = env_int("SMB200_PIPE_STAGES", 3);
             if (stages < 3) stages = 3;     // the kernel reads the descriptor of block i + 1 during iteration i

@@ -1,5 +1,7 @@
 """GPU, one process per GPU (needs >= 2 devices; skipped otherwise): the row-block distributed SpMV / dot / CG
-of libsmb200 (dist.cu, NCCL halo exchange + all-reduce) against the oracle's single-address-space results.
+of libsmb200 (dist.cu) against the oracle's single-address-space results, on both data paths: peer memory over NVLink
+(ghost entries stored into the neighbour's HBM by the product kernel, all-reduce through peer slots — halo.cuh) and the
+NCCL send/recv + all-reduce fallback.
 Partition contract: sparsemat_par.rs:20-35 (contiguous row blocks, every block needs the x entries its columns touch)."""
 import os
 import socket
@@ -22,8 +24,10 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, out_q):
+def _worker(rank, world, port, out_q, path):
     try:
+        os.environ["SMB200_DIST_P2P"] = "1" if path == "p2p" else "0"
+        os.environ.setdefault("SMB200_P2P_TIMEOUT_MS", "20000")
         sys.path.insert(0, ROOT)
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import torch.distributed as dist
@@ -42,6 +46,7 @@ def _worker(rank, world, port, out_q):
             nx, ny, nz = 24, 20, 4 * world + 3
             n = nx * ny * nz
             a = smb.DistCRS.laplace(ctx, vdt, np.uint32, nx, ny, nz)
+            assert a.info()["p2p"] == (path == "p2p"), a.info()
             d = a.dims()
             lo, hi = d["row_lo"], d["row_lo"] + d["n_local"]
             vals, cols, offs = orc.laplace(vdt, np.uint32, nx, ny, nz)
@@ -86,6 +91,28 @@ def _worker(rank, world, port, out_q):
         for _ in range(3):                                               # repeated exchanges reuse the plan
             y = a.mvp(x)
             assert np.array_equal(y.to_numpy(), want[lo:hi]), "dist general spmv is not bit-exact"
+        assert not a.info()["peer_timeout"]
+
+        # ---- (3) banded short rows, uneven nnz-balanced blocks: the ring kernel with packed (non-contiguous) sends,
+        #          ghost windows and windows that straddle the end of the owned part; x changes between products --------
+        for vdt, idt in ((np.float32, np.uint32), (np.float64, np.uint64)):
+            n, _, vals, cols, offs = cases.banded(7, 30011, 700, 9, vdt, idt)
+            bounds = smb.partition_rows_by_nnz(offs, world)
+            lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+            o64 = offs.astype(np.int64)
+            a = smb.DistCRS.from_local_block(ctx, n, bounds, vals[o64[lo]:o64[hi]], cols[o64[lo]:o64[hi]],
+                                             (o64[lo:hi + 1] - o64[lo]).astype(idt))
+            assert a.local.plan_info()["variant_name"] == "ring", a.local.plan_info()
+            x, y = a.new_vec(), a.new_vec()
+            for rep in range(5):
+                xg = orc.uniform(vdt, 40 + rep, n)
+                want = orc.mvp(vals, cols, offs, xg)
+                x.upload(xg[lo:hi])
+                a.mvp(x, out=y)
+                assert np.array_equal(y.to_numpy(), want[lo:hi]), f"dist banded ring spmv is not bit-exact (rep {rep})"
+            inf = a.info()
+            assert not inf["peer_timeout"] and (path != "p2p" or inf["products"] == 5), inf
+            a.barrier()
         ctx.sync()
         dist.barrier()
         dist.destroy_process_group()
@@ -95,15 +122,16 @@ def _worker(rank, world, port, out_q):
         out_q.put((rank, "FAIL: " + repr(e) + "\n" + traceback.format_exc()))
 
 
-@pytest.mark.parametrize("world", [2, 4])
-def test_row_block_distributed_spmv_dot_cg(world):
+@pytest.mark.parametrize("path", ["p2p", "nccl"])
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_row_block_distributed_spmv_dot_cg(world, path):
     if n_gpus() < world:
         pytest.skip(f"needs {world} GPUs, have {n_gpus()}")
     import torch.multiprocessing as mp
     ctxm = mp.get_context("spawn")
     q = ctxm.Queue()
     port = _free_port()
-    procs = [ctxm.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctxm.Process(target=_worker, args=(r, world, port, q, path)) for r in range(world)]
     for p in procs:
         p.start()
     results = []
