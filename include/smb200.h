@@ -114,6 +114,9 @@ typedef struct {
     uint64_t stream_bytes;    /* bytes the planned kernel moves per product:
                                * algorithmic_bytes - (nnz_c16 + rows_o16)*(sizeof I - 2)                              */
     uint64_t rows_o16;        /* RING: rows whose offsets are streamed as 16-bit block-relative numbers               */
+    uint64_t plan_bytes;      /* device memory the plan holds beside the three CRS arrays (split points, x windows,
+                               * 16-bit columns / offsets, band parts)                                                */
+    double plan_ms;           /* host wall-clock time the plan took to build (once per matrix and variant)            */
 } smb200_plan_info;
 
 typedef struct {

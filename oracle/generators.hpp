@@ -91,5 +91,31 @@ void powerlaw_fill(std::uint64_t seed_col, std::uint64_t seed_val, std::uint64_t
     }
 }
 
+// SparseMatrix::mvp (sparsematrix.rs:146-158) restricted to a sample of rows of the IMPLICIT power-law matrix: row i is
+// regenerated from the seeds (same formulas as powerlaw_fill), summed in storage order with separate mul and add like the
+// reference, and |row|.|x| is returned beside it as the scale of the reordered-reduction tolerance.  Lets the full-size
+// C3 product (800 M non-zeros, never held on the host) be checked row by row.
+template <class T>
+void powerlaw_sample_mvp(std::uint64_t seed_len, std::uint64_t seed_col, std::uint64_t seed_val, std::uint64_t n_cols,
+                         std::uint64_t max_len, std::uint64_t n_sample, const std::uint64_t* rows, const T* x, T* y,
+                         double* abs_sum, std::uint64_t* lens) {
+    for (std::uint64_t s = 0; s < n_sample; ++s) {
+        const std::uint64_t i = rows[s];
+        const std::uint64_t len = powerlaw_row_len(seed_len, i, max_len);
+        T sum = T(0);
+        double a = 0.0;
+        for (std::uint64_t k = 0; k < len; ++k) {
+            const std::uint64_t c = rng2(seed_col, i, k) % n_cols;
+            const T v = static_cast<T>(pm1(rng2(seed_val, i, k)));
+            const T prod = x[c] * v;
+            sum += prod;
+            a += std::fabs(static_cast<double>(x[c]) * static_cast<double>(v));
+        }
+        y[s] = sum;
+        if (abs_sum) abs_sum[s] = a;
+        if (lens) lens[s] = len;
+    }
+}
+
 }  // namespace gen
 }  // namespace oracle

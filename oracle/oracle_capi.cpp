@@ -197,6 +197,11 @@ int orc_par_locate(std::uint64_t n_blocks, std::uint64_t max_rows, std::uint64_t
 }
 
 #define ORC_VEC(T, S)                                                                                              \
+    void orc_powerlaw_sample_mvp_##S(std::uint64_t seed_len, std::uint64_t seed_col, std::uint64_t seed_val,        \
+                                     std::uint64_t n_cols, std::uint64_t max_len, std::uint64_t n_sample,           \
+                                     const std::uint64_t* rows, const T* x, T* y, double* abs_sum,                  \
+                                     std::uint64_t* lens) {                                                         \
+        gen::powerlaw_sample_mvp<T>(seed_len, seed_col, seed_val, n_cols, max_len, n_sample, rows, x, y, abs_sum, lens); } \
     void orc_uniform_##S(std::uint64_t seed, std::uint64_t n, T* out) { gen::uniform_pm1<T>(seed, n, out); }        \
     T orc_dot_##S(std::uint64_t n, const T* x, const T* y) {                                                        \
         T s = T(0); for (std::uint64_t k = 0; k < n; ++k) s += x[k] * y[k]; return s; }                             \

@@ -107,6 +107,24 @@ def powerlaw(vdt, idt, n_rows, n_cols=None, seed_len=3, seed_col=4, seed_val=5, 
     return values, columns, offsets
 
 
+def powerlaw_sample_mvp(vdt, n_cols, rows, x, seed_len=3, seed_col=4, seed_val=5, max_len=1_000_000):
+    """The reference's mvp on a sample of rows of the implicit power-law matrix (regenerated from the seeds):
+    returns (y[rows], sum |a||x| per row, row lengths)."""
+    rows = np.ascontiguousarray(rows, np.uint64)
+    y = np.empty(rows.size, vdt)
+    ab = np.empty(rows.size, np.float64)
+    lens = np.empty(rows.size, np.uint64)
+    fn("orc_powerlaw_sample_mvp", suffix(vdt))(_u64(seed_len), _u64(seed_col), _u64(seed_val), _u64(n_cols), _u64(max_len),
+                                               _u64(rows.size), _p(rows), _p(x), _p(y), _p(ab), _p(lens))
+    return y, ab, lens
+
+
+def powerlaw_row_lens(n_rows, seed_len=3, max_len=1_000_000):
+    lens = np.empty(n_rows, np.uint64)
+    lib().orc_powerlaw_row_lens(_u64(seed_len), _u64(n_rows), _u64(max_len), _p(lens))
+    return lens
+
+
 # ---- the hot path -------------------------------------------------------------------------------------------
 def mvp(values, columns, offsets, x, threads: int = 1):
     """SparseMatrix::mvp over SparseMatCRS (sparsematrix.rs:146-158), raw arrays."""

@@ -135,6 +135,7 @@ struct SpmvPlan {
     // rebased to its band) with its own stream plan; owned by the plan
     std::vector<smb200_crs*> parts;
     uint64_t band_width = 0;
+    double build_ms = 0.0;              // host wall-clock time of the build
     bool built = false;
 };
 

@@ -27,6 +27,7 @@
 #include "halo.cuh"
 #include "reduce.cuh"
 
+#include <chrono>
 #include <cstdlib>
 
 namespace smb {
@@ -1266,8 +1267,39 @@ static smb200_status plan_build_range_impl(smb200_crs* m, SpmvPlan& p, int want_
 
 // AUTO: short-row matrices try the TMA ring first (it also wins on the L2-resident C1: 12.3 us warm / 24.0 us cold); it is kept when (almost) every block got its
 // x windows (stencils, banded, FEM-like), otherwise the stream kernel — which gathers x through L1/L2 — is planned.
+static smb200_status plan_build_range_auto(smb200_crs* m, SpmvPlan& p, int want_variant, int want_lanes, uint32_t flags,
+                                           uint64_t rb, uint64_t re);
+
 smb200_status plan_build_range(smb200_crs* m, SpmvPlan& p, int want_variant, int want_lanes, uint32_t flags,
                                uint64_t rb, uint64_t re) {
+    const auto t0 = std::chrono::steady_clock::now();
+    const smb200_status st = plan_build_range_auto(m, p, want_variant, want_lanes, flags, rb, re);
+    if (st == SMB200_OK) {
+        cudaStreamSynchronize(m->ctx->stream);
+        p.build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+    return st;
+}
+
+// Device memory a plan holds beside the CRS arrays.
+static uint64_t plan_device_bytes(const smb200_crs* m, const SpmvPlan& p) {
+    const uint64_t is = isize(m->it);
+    uint64_t b = 0;
+    if (p.blk_rows) b += (p.n_blocks + 1) * is;
+    if (p.blk_nnz) b += (p.n_blocks + 1) * is;
+    if (p.blk_flags) b += p.n_blocks;
+    if (p.seg_lo) b += (uint64_t)kNSeg * p.n_blocks * 8;
+    if (p.seg_len) b += (uint64_t)kNSeg * p.n_blocks * 4;
+    if (p.lcols) b += (p.n_c16 ? p.n_c16 : m->nnz) * 2 + kPadBytes;
+    if (p.loffs) b += (p.n_o16 + 8 * p.n_blocks + 16) * 2 + kPadBytes;
+    if (p.blk_win) b += 2 * p.n_blocks * is;
+    for (const smb200_crs* part : p.parts)
+        b += part->nnz * (vsize(part->vt) + isize(part->it)) + (part->n_rows + 1) * isize(part->it) + plan_device_bytes(part, part->plan);
+    return b;
+}
+
+static smb200_status plan_build_range_auto(smb200_crs* m, SpmvPlan& p, int want_variant, int want_lanes, uint32_t flags,
+                                           uint64_t rb, uint64_t re) {
     int want = want_variant;
     if (want == SMB200_SPMV_AUTO) want = env_int("SMB200_SPMV_VARIANT", SMB200_SPMV_AUTO);
     if (want == SMB200_SPMV_AUTO && m->max_row_len <= (uint64_t)kRowMajorMax && m->nnz > 0) {
@@ -1815,6 +1847,8 @@ smb200_status smb200_crs_plan_info(const smb200_crs* cm, smb200_plan_info* out) 
     out->rows_o16 = m->plan.n_o16;
     out->stream_bytes = out->algorithmic_bytes - (m->plan.n_c16 + m->plan.n_o16) * (isize(m->it) - 2);
     if (m->plan.variant == SMB200_SPMV_BANDSPLIT) out->stream_bytes = bandsplit_stream_bytes(m, m->plan);
+    out->plan_bytes = plan_device_bytes(m, m->plan);
+    out->plan_ms = m->plan.build_ms;
     return SMB200_OK;
 }
 
