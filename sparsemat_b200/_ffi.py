@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libsmb200.so")
+LIB_PATH = os.environ.get("SMB200_LIB") or os.path.join(_HERE, "lib", "libsmb200.so")   # SMB200_LIB: A/B builds of the same ABI
 
 OK, ERR_INVALID, ERR_DIM, ERR_CUDA, ERR_NOT_SQUARE, ERR_SIZE_MISMATCH, ERR_NCCL, ERR_UNSUPPORTED, ERR_OOM, ERR_IO = range(10)
 F32, F64 = 0, 1

@@ -123,11 +123,19 @@ static smb200_status bandsplit_typed(smb200_crs* m, SpmvPlan& p, uint64_t width,
     return SMB200_OK;
 }
 
-// Band width in elements: x_b should take about half of L2 (the other half buffers the streams on their way through).
+// Band width in elements.  Measured on B200 (scripts/probes/l2_gather_probe.cu, scripts/c3_sweep.py): random 8-byte
+// gathers keep hitting L2 up to a window of ~64 MB of the 126 MB while evict-first streams pass through it, and the product
+// is fastest with the fewest bands that respect that (C3: 6 bands of 64 MB 6.25 ms, 7 of 55 MB 6.28, 9 of 43 MB 7.7, 12 of
+// 32 MB 8.8): every extra band costs a read-modify-write of y and a pass over the row offsets.  So: the smallest number of
+// equal bands of at most 0.53 L2.
 uint64_t bandsplit_width(const smb200_crs* m) {
     const char* e = getenv("SMB200_BANDSPLIT_WIDTH");
     uint64_t w = (e && *e) ? strtoull(e, nullptr, 10) : 0;
-    if (w == 0) w = (uint64_t)(m->ctx->l2_bytes / 2) / vsize(m->vt);
+    if (w == 0) {
+        const uint64_t max_w = (uint64_t)((double)m->ctx->l2_bytes * 0.53) / vsize(m->vt);
+        const uint64_t nb = (m->n_cols + max_w - 1) / (max_w ? max_w : 1);
+        w = ((m->n_cols + (nb ? nb : 1) - 1) / (nb ? nb : 1) + 1023) / 1024 * 1024;
+    }
     w = w / 1024 * 1024;
     if (w < 1024) w = 1024;
     // no more than kMaxBands bands

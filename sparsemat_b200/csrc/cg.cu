@@ -35,13 +35,13 @@ constexpr int kCgThreads = 256;
 template <class T>
 __global__ void __launch_bounds__(kCgThreads)
 cg_init_kernel(const T* __restrict__ b, const T* __restrict__ ap, T* __restrict__ r, T* __restrict__ p, uint64_t n,
-               double* __restrict__ S, int rr_slot, double* __restrict__ partials, unsigned int* __restrict__ ticket) {
+               double* __restrict__ S, int rr_slot, double* __restrict__ partials, unsigned int* __restrict__ ticket, int vec_ok) {
     __shared__ double scratch[kCgThreads / 32 + 1];
     using V = typename Vec16<T>::type;
     constexpr int N = Vec16<T>::N;
     const uint64_t tid = blockIdx.x * (uint64_t)kCgThreads + threadIdx.x;
     const uint64_t stride = (uint64_t)gridDim.x * kCgThreads;
-    const uint64_t nvec = n / N;
+    const uint64_t nvec = vec_ok ? n / N : 0;      // a borrowed b / x (smb200_vec_wrap) may not be 16-byte aligned: element loop
     T lane_acc[N];
 #pragma unroll
     for (int k = 0; k < N; ++k) lane_acc[k] = T(0);
@@ -75,7 +75,7 @@ cg_init_kernel(const T* __restrict__ b, const T* __restrict__ ap, T* __restrict_
 template <class T>
 __global__ void __launch_bounds__(kCgThreads)
 cg_update_xr_kernel(T* __restrict__ x, T* __restrict__ r, const T* __restrict__ p, const T* __restrict__ ap, uint64_t n,
-                    double* __restrict__ S, int rr_slot, double* __restrict__ partials, unsigned int* __restrict__ ticket) {
+                    double* __restrict__ S, int rr_slot, double* __restrict__ partials, unsigned int* __restrict__ ticket, int vec_ok) {
     __shared__ double scratch[kCgThreads / 32 + 1];
     if (__ldcg(S + S_DONE) != 0.0) return;
     const T alpha = div_rn((T)__ldcg(S + S_RR), (T)(__ldcg(S + S_PAP) + __ldcg(S + S_PAP + 1) + __ldcg(S + S_PAP + 2)));
@@ -83,7 +83,7 @@ cg_update_xr_kernel(T* __restrict__ x, T* __restrict__ r, const T* __restrict__ 
     constexpr int N = Vec16<T>::N;
     const uint64_t tid = blockIdx.x * (uint64_t)kCgThreads + threadIdx.x;
     const uint64_t stride = (uint64_t)gridDim.x * kCgThreads;
-    const uint64_t nvec = n / N;
+    const uint64_t nvec = vec_ok ? n / N : 0;      // a borrowed b / x (smb200_vec_wrap) may not be 16-byte aligned: element loop
     T lane_acc[N];
 #pragma unroll
     for (int k = 0; k < N; ++k) lane_acc[k] = T(0);
@@ -192,8 +192,9 @@ smb200_status cg_prepare(smb200_ctx* ctx, CgWork& w, int vt, uint64_t n, uint64_
 smb200_status cg_init_launch(smb200_ctx* ctx, CgWork& w, int vt, const void* b, uint64_t n) {
     const unsigned g = cg_grid(ctx, n, vt);
     const int slot = ctx->world > 1 ? S_RR_LOCAL : S_RR_NEW;
-    if (vt == SMB200_F64) cg_init_kernel<double><<<g, kCgThreads, 0, ctx->stream>>>((const double*)b, (const double*)w.ap, (double*)w.r, (double*)w.p, n, w.scalars, slot, ctx->red_partials, ctx->red_ticket);
-    else cg_init_kernel<float><<<g, kCgThreads, 0, ctx->stream>>>((const float*)b, (const float*)w.ap, (float*)w.r, (float*)w.p, n, w.scalars, slot, ctx->red_partials, ctx->red_ticket);
+    const int vec_ok = ((uintptr_t)b & 15u) == 0 ? 1 : 0;
+    if (vt == SMB200_F64) cg_init_kernel<double><<<g, kCgThreads, 0, ctx->stream>>>((const double*)b, (const double*)w.ap, (double*)w.r, (double*)w.p, n, w.scalars, slot, ctx->red_partials, ctx->red_ticket, vec_ok);
+    else cg_init_kernel<float><<<g, kCgThreads, 0, ctx->stream>>>((const float*)b, (const float*)w.ap, (float*)w.r, (float*)w.p, n, w.scalars, slot, ctx->red_partials, ctx->red_ticket, vec_ok);
     count_launch();
     SMB_CUDA(cudaGetLastError());
     return SMB200_OK;
@@ -202,8 +203,9 @@ smb200_status cg_init_launch(smb200_ctx* ctx, CgWork& w, int vt, const void* b, 
 smb200_status cg_xr_launch(smb200_ctx* ctx, CgWork& w, int vt, void* x, uint64_t n) {
     const unsigned g = cg_grid(ctx, n, vt);
     const int slot = ctx->world > 1 ? S_RR_LOCAL : S_RR_NEW;
-    if (vt == SMB200_F64) cg_update_xr_kernel<double><<<g, kCgThreads, 0, ctx->stream>>>((double*)x, (double*)w.r, (const double*)w.p, (const double*)w.ap, n, w.scalars, slot, ctx->red_partials, ctx->red_ticket);
-    else cg_update_xr_kernel<float><<<g, kCgThreads, 0, ctx->stream>>>((float*)x, (float*)w.r, (const float*)w.p, (const float*)w.ap, n, w.scalars, slot, ctx->red_partials, ctx->red_ticket);
+    const int vec_ok = ((uintptr_t)x & 15u) == 0 ? 1 : 0;
+    if (vt == SMB200_F64) cg_update_xr_kernel<double><<<g, kCgThreads, 0, ctx->stream>>>((double*)x, (double*)w.r, (const double*)w.p, (const double*)w.ap, n, w.scalars, slot, ctx->red_partials, ctx->red_ticket, vec_ok);
+    else cg_update_xr_kernel<float><<<g, kCgThreads, 0, ctx->stream>>>((float*)x, (float*)w.r, (const float*)w.p, (const float*)w.ap, n, w.scalars, slot, ctx->red_partials, ctx->red_ticket, vec_ok);
     count_launch();
     SMB_CUDA(cudaGetLastError());
     return SMB200_OK;

@@ -200,10 +200,13 @@ extern thread_local int g_ring_reserve_sms;
 extern thread_local int g_ring_grid_cap;
 // Set while the second and later bands of a band-split product are launched: the stream kernel adds to y instead of writing it.
 extern thread_local bool g_spmv_accumulate;
+// Set while the bands of a band-split product are launched: the stream plan of a part runs spmv_band_kernel (L2 eviction
+// hints that keep the band of x resident, prefetched y).
+extern thread_local bool g_spmv_band;
 // Set by dist.cu around the ONE ring launch of a distributed product: the kernel then also runs the halo protocol of
 // halo.cuh (push the neighbours' ghost entries, wait for this rank's) and walks the row blocks rotated by `rot`.
 struct HaloDev;
-struct HaloLaunch { const HaloDev* dev = nullptr; uint64_t rot = 0; };
+struct HaloLaunch { const HaloDev* host = nullptr; uint64_t rot = 0; };     // host copy: passed to the kernel by value
 extern thread_local HaloLaunch g_halo;
 // Set while an SpMV reads a caller-owned (smb200_vec_wrap) vector: such memory has no padding behind its last element,
 // so kernels must not round bulk copies of it up to 16 bytes.

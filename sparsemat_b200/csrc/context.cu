@@ -9,6 +9,7 @@ thread_local LaunchRedirect g_redirect;
 thread_local int g_ring_reserve_sms = 0;
 thread_local int g_ring_grid_cap = 0;
 thread_local bool g_spmv_accumulate = false;
+thread_local bool g_spmv_band = false;
 thread_local bool g_x_unpadded = false;
 thread_local HaloLaunch g_halo;
 

@@ -394,6 +394,11 @@ smb200_status smb200_crs_scale(smb200_crs* m, double s) {
     else scale_values_kernel<float><<<g, 256, 0, m->ctx->stream>>>((float*)m->values, m->nnz, (float)s);
     count_launch();
     SMB_CUDA(cudaGetLastError());
+    // a band-split plan multiplies its own copies of the values (bandsplit.cu): they are scaled with the matrix, so that
+    // `scale` affects every later product as in the reference (sparsemat_crs.rs:153-157)
+    for (smb200_crs* part : m->plan.parts) SMB_TRY(smb200_crs_scale(part, s));
+    for (auto& hp : m->hp.plans)
+        for (smb200_crs* part : hp.parts) SMB_TRY(smb200_crs_scale(part, s));
     return SMB200_OK;
 }
 

@@ -101,10 +101,7 @@ __global__ void __launch_bounds__(256) halo_push_kernel(const HaloDev* __restric
     const unsigned long long e = __ldcg(h->epoch) + 1ull;
     halo_push<T>(*h, x, e, blockIdx.x * (uint64_t)blockDim.x + threadIdx.x, (uint64_t)gridDim.x * blockDim.x);
     __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        if (atomicAdd(h->ctr, 1u) == gridDim.x - 1) { h->ctr[0] = 0u; halo_signal(*h, e); }
-    }
+    if (threadIdx.x == 0) halo_arrive(*h, e, gridDim.x);
 }
 
 template <class T>
@@ -191,11 +188,13 @@ struct smb200_dist {
     void* win = nullptr;                          // this rank's window: flags | all-reduce flags | all-reduce slots | ghost double buffer
     std::vector<void*> peer_base;                 // the peers' windows mapped here (nullptr: self / not mapped)
     void* misc = nullptr;                         // local words: halo epoch, all-reduce epoch, arrival counters, error
-    smb::HaloDev* h_dev = nullptr;
+    smb::HaloDev* h_dev = nullptr;                // device copy (the small push / wait kernels read it)
+    smb::HaloDev h_host;                          // host copy (the ring kernel takes it by value)
     smb::ArDev* ar_dev = nullptr;
     double* ar_scratch = nullptr;                 // [2 * kArSlots] operands of barriers / dots
     uint64_t rot = 0;                             // ring block order: first block without lower-ghost rows
     int n_nbr = 0;
+    bool self_halo = false;                       // SMB200_DIST_SELF: world == 1 through the distributed kernel path
 };
 
 namespace smb {
@@ -223,6 +222,7 @@ static smb200_status dist_build_plans(smb200_dist* d) {
 }
 
 static bool dist_exchanges(const smb200_dist* d) {
+    if (d->self_halo) return true;
     return !(d->ctx->world == 1 || (d->n_ghost == 0 && d->total_send == 0));
 }
 
@@ -262,7 +262,33 @@ static smb200_status dist_p2p_setup(smb200_dist* d) {
     smb200_ctx* ctx = d->ctx;
     const int world = ctx->world, me = ctx->rank;
     d->p2p = false;
-    if (world == 1) return SMB200_OK;
+    if (world == 1) {
+        // SMB200_DIST_SELF=1 (measurements only): run the distributed kernel path with zero neighbours on one GPU, which
+        // isolates what the halo code itself costs from what the coupling of the ranks costs
+        const char* self = getenv("SMB200_DIST_SELF");
+        if (!(self && self[0] == '1')) return SMB200_OK;
+        SMB_CUDA(cudaMalloc(&d->misc, 256));
+        SMB_CUDA(cudaMemset(d->misc, 0, 256));
+        SMB_CUDA(cudaMalloc(&d->win, 4096));
+        SMB_CUDA(cudaMemset(d->win, 0, 4096));
+        HaloDev h;
+        memset(&h, 0, sizeof h);
+        unsigned char* misc = (unsigned char*)d->misc;
+        h.epoch = (unsigned long long*)(misc + 0);
+        h.ctr = (unsigned*)(misc + 16);
+        h.error = (unsigned*)(misc + 24);
+        h.flags = (unsigned long long*)d->win;
+        h.ghost = (unsigned char*)d->win + 256;
+        h.ghost_stride = 64;
+        h.g0 = d->g0;
+        h.timeout_ns = 1000000000ull;
+        SMB_CUDA(cudaMalloc(&d->h_dev, sizeof h));
+        SMB_CUDA(cudaMemcpy(d->h_dev, &h, sizeof h, cudaMemcpyHostToDevice));
+        d->h_host = h;
+        d->p2p = true;
+        d->self_halo = true;
+        return SMB200_OK;
+    }
     ncclComm_t comm = (ncclComm_t)ctx->comm;
     const size_t es = vsize(d->vt);
     const char* env = getenv("SMB200_DIST_P2P");
@@ -374,6 +400,7 @@ static smb200_status dist_p2p_setup(smb200_dist* d) {
     SMB_CUDA(cudaMalloc(&d->ar_dev, sizeof a));
     SMB_CUDA(cudaMalloc(&d->ar_scratch, 2 * kArSlots * sizeof(double)));
     SMB_CUDA(cudaMemcpy(d->h_dev, &h, sizeof h, cudaMemcpyHostToDevice));
+    d->h_host = h;
     SMB_CUDA(cudaMemcpy(d->ar_dev, &a, sizeof a, cudaMemcpyHostToDevice));
     SMB_CUDA(cudaMemset(d->ar_scratch, 0, 2 * kArSlots * sizeof(double)));
     d->p2p = true;
@@ -455,7 +482,7 @@ static smb200_status dist_spmv_impl(smb200_dist* d, void* x, void* y, double* S)
     if (exchange && d->p2p) {
         if (m->plan.built && m->plan.variant == SMB200_SPMV_RING) {
             // ONE launch: push, interior blocks, wait, boundary blocks (spmv_ring_kernel's halo path)
-            g_halo.dev = d->h_dev;
+            g_halo.host = &d->h_host;
             g_halo.rot = d->rot;
             const smb200_status st = S ? spmv_launch_cg(m, m->plan, 0, d->n_local, x, y, x, S, 0, true)
                                        : spmv_launch_plan(m, m->plan, 0, d->n_local, x, y, nullptr, 0);

@@ -70,7 +70,7 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 }
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
-// Step 1, data: thread `tid` of `nthreads` copies its share of the entries the neighbours need.
+// Step 1, data: thread `tid` of `nthreads` copies its share of the entries the neighbours need (plain stores; see halo_arrive).
 template <class T>
 __device__ __forceinline__ void halo_push(const HaloDev& h, const T* __restrict__ x, unsigned long long e, uint64_t tid, uint64_t nthreads) {
     const int n = h.n_nbr;
@@ -86,7 +86,14 @@ __device__ __forceinline__ void halo_push(const HaloDev& h, const T* __restrict_
             for (unsigned long long k = tid; k < cnt; k += nthreads) dst[k] = x[idx[k]];
         }
     }
+}
+// The caller then joins its pushing threads with a CTA-level barrier and ONE of them calls halo_arrive: its system-scope
+// fence is cumulative over the stores the barrier made visible to it (the pattern of a grid-wide barrier), so the 100k
+// pushing threads need no fence of their own.
+__device__ __forceinline__ void halo_signal(const HaloDev& h, unsigned long long e);
+__device__ __forceinline__ void halo_arrive(const HaloDev& h, unsigned long long e, unsigned n_ctas) {
     __threadfence_system();
+    if (atomicAdd(h.ctr, 1u) == n_ctas - 1) { h.ctr[0] = 0u; halo_signal(h, e); }
 }
 
 // Step 1, flags: one thread, after every pushing thread of the grid has fenced and arrived.

@@ -142,6 +142,45 @@ template <class E> __device__ __forceinline__ Quad<E> load_quad_stream(const E* 
     }
     return q;
 }
+// Band-split products (bandsplit.cu): the band of x being gathered must stay in L2 while everything else streams past
+// it, so the streams are marked evict-first in L2 (4-byte quads too) and the gathers evict-last.
+// (The .L2::evict_* qualifiers exist for 256-bit loads only; narrower accesses take a policy operand.)
+struct L2Policy { uint64_t first, last; };
+__device__ __forceinline__ L2Policy make_l2_policies() {
+    L2Policy p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p.first));
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p.last));
+    return p;
+}
+template <class E> __device__ __forceinline__ Quad<E> load_quad_evict_first(const E* p, uint64_t pol) {
+    if constexpr (sizeof(E) == 4) {
+        Quad<E> q;
+        uint4 v;
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                     : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
+        memcpy(q.e, &v, 16);
+        return q;
+    } else {
+        return load_quad_stream(p);
+    }
+}
+template <class T> __device__ __forceinline__ T gather_hint(const T* p, uint64_t pol) {
+    T v;
+    if constexpr (sizeof(T) == 8) asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+    else asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+    return v;
+}
+template <class T> __device__ __forceinline__ T load_hint(const T* p, uint64_t pol) {
+    T v;
+    if constexpr (sizeof(T) == 8) asm volatile("ld.global.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol) : "memory");
+    else asm volatile("ld.global.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol) : "memory");
+    return v;
+}
+template <class T> __device__ __forceinline__ void store_hint(T* p, T v, uint64_t pol) {
+    if constexpr (sizeof(T) == 8) asm volatile("st.global.L1::no_allocate.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
+    else asm volatile("st.global.L1::no_allocate.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
+}
+
 template <class E> __device__ __forceinline__ Quad<E> load_quad_shared(const E* p) {
     Quad<E> q;
     if constexpr (sizeof(E) == 4) {
@@ -348,6 +387,101 @@ spmv_stream_kernel(const T* __restrict__ vals, const I* __restrict__ cols, const
         if (r_next < r1)
             acc += reduce_rows_from_smem<T, I, DOT>(prod, offs, r_next, r1, a0 + 0, y, (const T*)dot.w, &s_long_count, s_long_rows, accumulate != 0);
     } else {
+        acc = rows_direct<T, I, DOT>(vals, cols, offs, r0, r1, x, y, (const T*)dot.w, &s_long_count, s_long_rows, scratch, accumulate != 0);
+    }
+    if constexpr (DOT) finish_dot<T>(acc, dot);
+}
+
+// ---- K3 for the column bands of a band-split product (bandsplit.cu) ------------------------------------
+// Same shape as spmv_stream_kernel, tuned for parts with 1-3 entries per row: the matrix streams (and y, which every band
+// but the first reads and all write) are evict-first in L2, the gathers evict-last, so the band of x survives; the row
+// offsets, the old y and the dot weights of up to KP rows per thread are requested before the stream phase; whether the
+// block takes the one-thread-per-row pass or the generic two-pass one is voted BEFORE anything is written (y += must
+// happen once).
+template <class T, class I, bool DOT>
+__global__ void __launch_bounds__(kSpmvThreads, 4)
+spmv_band_kernel(const T* __restrict__ vals, const I* __restrict__ cols, const I* __restrict__ offs,
+                 const I* __restrict__ blk_rows, const I* __restrict__ blk_nnz, unsigned cap, const T* __restrict__ x,
+                 T* __restrict__ y, DotArgs dot, int accumulate) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    T* prod = reinterpret_cast<T*>(smem_raw);
+    __shared__ unsigned int s_long_count;
+    __shared__ unsigned int s_long_rows[kLongCap];
+    __shared__ double scratch[kSpmvThreads / 32 + 1];
+    if (threadIdx.x == 0) s_long_count = 0;
+    const uint64_t r0 = (uint64_t)__ldg(blk_rows + blockIdx.x), r1 = (uint64_t)__ldg(blk_rows + blockIdx.x + 1);
+    const uint64_t n0 = (uint64_t)__ldg(blk_nnz + blockIdx.x), n1 = (uint64_t)__ldg(blk_nnz + blockIdx.x + 1);
+    double stop = 0.0;
+    if constexpr (DOT) { if (dot.done != nullptr) stop = __ldcg(dot.done); }
+    const uint64_t a0 = n0 & ~(uint64_t)3;
+    if constexpr (DOT) { if (stop != 0.0) return; }
+    const L2Policy pol = make_l2_policies();
+    constexpr int KP = 4;
+    I pfa[KP], pfe[KP];
+    T pfy[KP], pfw[KP];
+#pragma unroll
+    for (int j = 0; j < KP; ++j) {
+        const uint64_t r = r0 + threadIdx.x + (uint64_t)j * kSpmvThreads;
+        pfa[j] = pfe[j] = 0;
+        pfy[j] = pfw[j] = T(0);
+        if (r < r1) {
+            pfa[j] = __ldg(offs + r); pfe[j] = __ldg(offs + r + 1);
+            if (accumulate) pfy[j] = load_hint(y + r, pol.first);
+            if constexpr (DOT) pfw[j] = __ldg((const T*)dot.w + r);
+        }
+    }
+    double acc = 0.0;
+    if (n1 - a0 <= (uint64_t)cap) {
+        const unsigned groups = (unsigned)((n1 - a0 + 3) >> 2);
+        const T* vbase = vals + a0;
+        const I* cbase = cols + a0;
+        unsigned g = threadIdx.x;
+        for (; g + kSpmvThreads < groups; g += 2 * kSpmvThreads) {
+            const Quad<I> c0 = load_quad_evict_first(cbase + 4 * (size_t)g, pol.first);
+            const Quad<I> c1 = load_quad_evict_first(cbase + 4 * (size_t)(g + kSpmvThreads), pol.first);
+            const Quad<T> v0 = load_quad_evict_first(vbase + 4 * (size_t)g, pol.first);
+            const Quad<T> v1 = load_quad_evict_first(vbase + 4 * (size_t)(g + kSpmvThreads), pol.first);
+            Quad<T> p0, p1;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) p0.e[k] = gather_hint(x + (size_t)c0.e[k], pol.last);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) p1.e[k] = gather_hint(x + (size_t)c1.e[k], pol.last);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { p0.e[k] = mul_rn(p0.e[k], v0.e[k]); p1.e[k] = mul_rn(p1.e[k], v1.e[k]); }
+            store_quad_shared(prod + 4 * g, p0);
+            store_quad_shared(prod + 4 * (g + kSpmvThreads), p1);
+        }
+        if (g < groups) {
+            const Quad<I> c0 = load_quad_evict_first(cbase + 4 * (size_t)g, pol.first);
+            const Quad<T> v0 = load_quad_evict_first(vbase + 4 * (size_t)g, pol.first);
+            Quad<T> p0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) p0.e[k] = mul_rn(gather_hint(x + (size_t)c0.e[k], pol.last), v0.e[k]);
+            store_quad_shared(prod + 4 * g, p0);
+        }
+        // vote: every row of the block is among the prefetched ones and short enough for the storage-order sum
+        bool mine_ok = true;
+#pragma unroll
+        for (int j = 0; j < KP; ++j) mine_ok = mine_ok && ((uint64_t)pfe[j] - (uint64_t)pfa[j] <= (uint64_t)kWarpRowMin);
+        const bool generic = __syncthreads_or(!mine_ok || (r1 - r0) > (uint64_t)KP * kSpmvThreads) != 0;   // (also: products are in place)
+        if (!generic) {
+#pragma unroll
+            for (int j = 0; j < KP; ++j) {
+                const uint64_t r = r0 + threadIdx.x + (uint64_t)j * kSpmvThreads;
+                if (r < r1) {
+                    const unsigned a = (unsigned)((uint64_t)pfa[j] - a0), e = (unsigned)((uint64_t)pfe[j] - a0);
+                    T sum = T(0);
+                    for (unsigned k = a; k < e; ++k) sum = add_rn(sum, prod[k]);
+                    if (accumulate) sum = add_rn(pfy[j], sum);
+                    store_hint(y + r, sum, pol.first);
+                    if constexpr (DOT) acc += (double)mul_rn(pfw[j], sum);
+                }
+            }
+        } else {
+            acc = reduce_rows_from_smem<T, I, DOT>(prod, offs, r0, r1, a0, y, (const T*)dot.w, &s_long_count, s_long_rows, accumulate != 0);
+        }
+    } else {
+        __syncthreads();
         acc = rows_direct<T, I, DOT>(vals, cols, offs, r0, r1, x, y, (const T*)dot.w, &s_long_count, s_long_rows, scratch, accumulate != 0);
     }
     if constexpr (DOT) finish_dot<T>(acc, dot);
@@ -744,7 +878,7 @@ __device__ __forceinline__ void ring_row_span(const I* so, uint64_t r, uint64_t 
     }
 }
 
-template <class T, class I, bool DOT, int NSEG, bool O16 = false>
+template <class T, class I, bool DOT, int NSEG, bool O16 = false, bool DIST = false>
 __device__ __forceinline__ double ring_rows(const T* sv, const I* sc, const I* so, const T* sx, const RingDesc& d,
                                             unsigned lane_id, unsigned n_lanes, const T* __restrict__ x, T* __restrict__ y,
                                             const T* __restrict__ w, const T* gx = nullptr, unsigned long long g0 = ~0ull) {
@@ -764,7 +898,8 @@ __device__ __forceinline__ double ring_rows(const T* sv, const I* sc, const I* s
             const I c = sc[k];
             T xv;
             if constexpr (NSEG > 0) xv = sx[win.at(c)];
-            else xv = (unsigned long long)c >= g0 ? __ldcg(gx + ((unsigned long long)c - g0)) : __ldg(x + (size_t)c);   // ghosts: written by peers during this launch
+            else if constexpr (DIST) xv = (unsigned long long)c >= g0 ? __ldcg(gx + ((unsigned long long)c - g0)) : __ldg(x + (size_t)c);   // ghosts: written by peers during this launch
+            else xv = __ldg(x + (size_t)c);
             sum = add_rn(sum, mul_rn(xv, sv[k]));
         }
         y[r] = sum;
@@ -795,14 +930,18 @@ __device__ __forceinline__ double ring_rows_c16(const T* sv, const uint16_t* sc,
     return acc;
 }
 
-template <class T, class I, bool DOT>
+// DIST = true: the launch is one distributed product (halo protocol of halo.cuh); false compiles all of it out.
+struct NoHalo {};
+template <bool DIST> struct HaloParam { using type = NoHalo; };
+template <> struct HaloParam<true> { using type = HaloDev; };       // by value: its fields are read from the constant bank
+template <class T, class I, bool DOT, bool DIST>
 __global__ void __launch_bounds__(kRingThreads, 2)
 spmv_ring_kernel(const T* __restrict__ vals, const I* __restrict__ cols, const I* __restrict__ offs,
                  const I* __restrict__ blk_rows, const I* __restrict__ blk_nnz, const unsigned long long* __restrict__ seg_lo,
                  const unsigned* __restrict__ seg_len, unsigned n_blocks, unsigned cap, unsigned ocap, unsigned xcap,
                  unsigned colb, unsigned stages, int xwin_ok, const uint16_t* __restrict__ lcols, unsigned long long lcols_base,
                  const uint16_t* __restrict__ loffs, unsigned long long row_begin, const T* __restrict__ x, T* __restrict__ y,
-                 DotArgs dot, const HaloDev* __restrict__ halo, unsigned rot) {
+                 DotArgs dot, const typename HaloParam<DIST>::type halo, unsigned rot) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full[kPipeMaxStages];    // producer -> consumers: the stage's bytes have landed
     __shared__ __align__(8) uint64_t empty[kPipeMaxStages];   // consumers -> producer: every consumer warp has left the stage
@@ -822,33 +961,49 @@ spmv_ring_kernel(const T* __restrict__ vals, const I* __restrict__ cols, const I
         for (unsigned s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kConsumerWarps); }
     // Distributed product (dist.cu, halo.cuh): this launch is epoch `epoch` of the halo protocol.  The ghost entries of x
     // live in half `epoch & 1` of the rank's ghost buffer, written by the neighbours' launches of the same epoch.
-    const bool dist = halo != nullptr;
     unsigned long long epoch = 0, g0 = ~0ull;
     const T* gx = nullptr;
-    if (dist) {
-        epoch = __ldcg(halo->epoch) + 1ull;
-        g0 = halo->g0;
-        gx = (const T*)halo->ghost + (epoch & 1ull) * halo->ghost_stride;
+    if constexpr (DIST) {
+        epoch = __ldcg(halo.epoch) + 1ull;            // one L2 round trip, first needed by the push / the first ghost block
+        g0 = halo.g0;
+        gx = (const T*)halo.ghost + (epoch & 1ull) * halo.ghost_stride;
     }
-    bool waited = false;                     // producer lane: the neighbours' flags of this epoch have been seen
+    [[maybe_unused]] bool waited = false;    // producer lane: the neighbours' flags of this epoch have been seen
     __syncthreads();
     double acc = 0.0;
 
     if (tid < 32) {
         // ---- producer warp: lane 0 runs ahead of the consumers, bounded only by the ring depth --------------------------
         if (tid == 0) {
-            unsigned s = 0, parity = 0;
-            for (unsigned j = 0; j < n_my; ++j) {
+            // The producer is ONE thread and every block costs it a round trip for the block's metadata plus a few hundred
+            // instructions; with two stages it must stay well below the ~1.9 us the consumers need per block.  The distributed
+            // instantiation (more work per block) requests the metadata of block j + 1 while block j is being issued.
+            struct Meta { I r0, r1, n0, n1; unsigned long long lo[kNSeg]; unsigned len[kNSeg]; size_t b; };
+            auto fetch = [&](unsigned j) {
+                Meta m;
                 // `rot` rotates the block order so that the rows that need ghost entries come last (their wait is then over
                 // before it starts)
-                size_t b = (size_t)blockIdx.x + (size_t)j * gridDim.x + rot;
-                if (b >= n_blocks) b -= n_blocks;
-                const unsigned long long r0 = (unsigned long long)__ldg(blk_rows + b), r1 = (unsigned long long)__ldg(blk_rows + b + 1);
-                const unsigned long long n0 = (unsigned long long)__ldg(blk_nnz + b), n1 = (unsigned long long)__ldg(blk_nnz + b + 1);
-                unsigned long long lo[kNSeg];
-                unsigned len[kNSeg];
+                size_t b = (size_t)blockIdx.x + (size_t)j * gridDim.x;
+                if constexpr (DIST) { b += rot; if (b >= n_blocks) b -= n_blocks; }
+                m.b = b;
+                m.r0 = __ldg(blk_rows + b); m.r1 = __ldg(blk_rows + b + 1);
+                m.n0 = __ldg(blk_nnz + b); m.n1 = __ldg(blk_nnz + b + 1);
 #pragma unroll
-                for (int i = 0; i < kNSeg; ++i) { lo[i] = __ldg(seg_lo + kNSeg * b + i); len[i] = __ldg(seg_len + kNSeg * b + i); }
+                for (int i = 0; i < kNSeg; ++i) { m.lo[i] = __ldg(seg_lo + kNSeg * b + i); m.len[i] = __ldg(seg_len + kNSeg * b + i); }
+                return m;
+            };
+            unsigned s = 0, parity = 0;
+            [[maybe_unused]] Meta next;
+            if constexpr (DIST) next = fetch(0);
+            for (unsigned j = 0; j < n_my; ++j) {
+                // (measured on the 256^3 f32 slab: the look-ahead takes the distributed launch from 136.5 to 133.3 us, but
+                // costs the plain one 3 us — 131.2 instead of 128.2 —, so only the distributed instantiation uses it)
+                Meta cur;
+                if constexpr (DIST) { cur = next; if (j + 1 < n_my) next = fetch(j + 1); }
+                else cur = fetch(j);
+                const size_t b = cur.b;
+                const unsigned long long r0 = (unsigned long long)cur.r0, r1 = (unsigned long long)cur.r1;
+                const unsigned long long n0 = (unsigned long long)cur.n0, n1 = (unsigned long long)cur.n1;
                 if (j >= stages) mbar_wait(&empty[s], parity ^ 1u);     // the consumers have drained this stage's previous block
                 RingDesc& d = s_desc[s];
                 unsigned char* base = smem_raw + (size_t)s * stage_bytes;
@@ -862,12 +1017,14 @@ spmv_ring_kernel(const T* __restrict__ vals, const I* __restrict__ cols, const I
                 const unsigned obytes = ocount * (o16 ? 2u : (unsigned)sizeof(I));
                 d.r0 = r0; d.r1 = r1; d.a0 = a0; d.r0a = r0a; d.o16 = o16 ? 1u : 0u;
                 unsigned xtotal = 0, nseg = 0;
+                [[maybe_unused]] bool need = false;     // DIST: the block reads ghost entries
 #pragma unroll
                 for (int i = 0; i < kNSeg; ++i) {
-                    d.lo[i] = len[i] ? lo[i] : ~0ull;
-                    d.delta[i] = (long long)xtotal - (long long)lo[i];
-                    xtotal += len[i];
-                    nseg += len[i] ? 1u : 0u;
+                    d.lo[i] = cur.len[i] ? cur.lo[i] : ~0ull;
+                    d.delta[i] = (long long)xtotal - (long long)cur.lo[i];
+                    xtotal += cur.len[i];
+                    nseg += cur.len[i] ? 1u : 0u;
+                    if constexpr (DIST) need = need || (cur.len[i] != 0u && cur.lo[i] + cur.len[i] > g0);
                 }
                 const bool xw = xwin_ok && xtotal > 0;
                 const bool c16 = xw && lcols != nullptr;
@@ -876,12 +1033,15 @@ spmv_ring_kernel(const T* __restrict__ vals, const I* __restrict__ cols, const I
                 const unsigned cbytes = count * (c16 ? 2u : (unsigned)sizeof(I));
                 unsigned bytes = count * (unsigned)sizeof(T) + cbytes + obytes;
                 if (xw) bytes += xtotal * (unsigned)sizeof(T);
-                if (dist && !waited) {
-                    // a block without windows gathers any column; a windowed one needs the ghosts if a window reaches past g0
-                    bool need = !xw;
-#pragma unroll
-                    for (int i = 0; i < kNSeg; ++i) need = need || (len[i] != 0u && lo[i] + len[i] > g0);
-                    if (need) { halo_wait(*halo, epoch); fence_proxy_async_global(); waited = true; }
+                if constexpr (DIST) {
+                    // A block without windows gathers any column, a windowed one needs the ghosts if a window reaches past g0;
+                    // and a product ends only after every neighbour's flag of its epoch was seen (halo.cuh, step 3): CTA 0
+                    // waits at its last block at the latest.
+                    if (!waited && (need || !xw || (blockIdx.x == 0 && j + 1 == n_my))) {
+                        halo_wait(halo, epoch);
+                        fence_proxy_async_global();
+                        waited = true;
+                    }
                 }
                 mbar_expect_tx(&full[s], bytes);
                 if (count) {
@@ -895,37 +1055,35 @@ spmv_ring_kernel(const T* __restrict__ vals, const I* __restrict__ cols, const I
                     unsigned at = 0;
 #pragma unroll
                     for (int i = 0; i < kNSeg; ++i)
-                        if (len[i]) {
+                        if (cur.len[i]) {
                             unsigned char* dstw = base + o_x + (size_t)at * sizeof(T);
-                            if (lo[i] + len[i] <= g0) {                    // owned entries (always, when not distributed)
-                                bulk_g2s(dstw, x + lo[i], len[i] * (unsigned)sizeof(T), &full[s]);
-                            } else if (lo[i] >= g0) {                      // ghost entries: this epoch's half of the ghost buffer
-                                bulk_g2s(dstw, gx + (lo[i] - g0), len[i] * (unsigned)sizeof(T), &full[s]);
-                            } else {                                       // a window across the end of the owned part (g0 is 16-byte aligned)
-                                const unsigned n1 = (unsigned)(g0 - lo[i]);
-                                bulk_g2s(dstw, x + lo[i], n1 * (unsigned)sizeof(T), &full[s]);
-                                bulk_g2s(dstw + (size_t)n1 * sizeof(T), gx, (len[i] - n1) * (unsigned)sizeof(T), &full[s]);
+                            if constexpr (!DIST) {
+                                bulk_g2s(dstw, x + cur.lo[i], cur.len[i] * (unsigned)sizeof(T), &full[s]);
+                            } else {
+                                // owned part of the window from x, ghost part from this epoch's half of the ghost buffer (a window
+                                // across the end of the owned columns is two copies: g0 is a multiple of 64 elements)
+                                const unsigned long long lo = cur.lo[i];
+                                const unsigned n_own = lo >= g0 ? 0u : (unsigned)(g0 - lo < (unsigned long long)cur.len[i] ? g0 - lo : cur.len[i]);
+                                if (n_own) bulk_g2s(dstw, x + lo, n_own * (unsigned)sizeof(T), &full[s]);
+                                if (cur.len[i] > n_own)
+                                    bulk_g2s(dstw + (size_t)n_own * sizeof(T), gx + (lo + n_own - g0), (cur.len[i] - n_own) * (unsigned)sizeof(T), &full[s]);
                             }
-                            at += len[i];
+                            at += cur.len[i];
                         }
                 }
                 if (++s == stages) { s = 0; parity ^= 1u; }
             }
-            // a product ends only after every neighbour's flag of its epoch was seen (halo.cuh, step 3)
-            if (dist && blockIdx.x == 0 && !waited) halo_wait(*halo, epoch);
         }
     } else {
         // ---- consumer warps: no block-wide barrier; a warp releases the stage as soon as its own rows are done ------------
         const unsigned lane_id = tid - 32, n_lanes = kRingThreads - 32;
-        if (dist) {
+        if constexpr (DIST) {
             // x is final (stream order): while the first stages are still in flight, put the entries the neighbours need into
-            // their ghost buffers; the CTA whose consumers finish last raises the neighbours' flags
-            halo_push<T>(*halo, x, epoch, (uint64_t)blockIdx.x * n_lanes + lane_id, (uint64_t)gridDim.x * n_lanes);
+            // their ghost buffers; the CTA whose consumers finish last raises the neighbours' flags.  (Measured: letting the
+            // 31 idle lanes of the producer warp do this instead slows lane 0 down — 0.145 vs 0.139 ms per product.)
+            halo_push<T>(halo, x, epoch, (uint64_t)blockIdx.x * n_lanes + lane_id, (uint64_t)gridDim.x * n_lanes);
             asm volatile("bar.sync 1, %0;" ::"r"(n_lanes) : "memory");
-            if (lane_id == 0) {
-                __threadfence();
-                if (atomicAdd(halo->ctr, 1u) == gridDim.x - 1) halo_signal(*halo, epoch);
-            }
+            if (lane_id == 0) halo_arrive(halo, epoch, gridDim.x);
         }
         unsigned s = 0, parity = 0;
         for (unsigned i = 0; i < n_my; ++i) {
@@ -943,8 +1101,8 @@ spmv_ring_kernel(const T* __restrict__ vals, const I* __restrict__ cols, const I
                 else acc += ring_rows_c16<T, I, DOT, false>(sv, sc16, so, sx, d, lane_id, n_lanes, y, w);
             } else switch (d.xwin) {              // number of x windows of the block (block-uniform)
                 case 0:
-                    if (d.o16) acc += ring_rows<T, I, DOT, 0, true>(sv, sc, so, sx, d, lane_id, n_lanes, x, y, w, gx, g0);
-                    else acc += ring_rows<T, I, DOT, 0, false>(sv, sc, so, sx, d, lane_id, n_lanes, x, y, w, gx, g0);
+                    if (d.o16) acc += ring_rows<T, I, DOT, 0, true, DIST>(sv, sc, so, sx, d, lane_id, n_lanes, x, y, w, gx, g0);
+                    else acc += ring_rows<T, I, DOT, 0, false, DIST>(sv, sc, so, sx, d, lane_id, n_lanes, x, y, w, gx, g0);
                     break;
                 case 1: acc += ring_rows<T, I, DOT, 1>(sv, sc, so, sx, d, lane_id, n_lanes, x, y, w); break;
                 case 2: acc += ring_rows<T, I, DOT, 2>(sv, sc, so, sx, d, lane_id, n_lanes, x, y, w); break;
@@ -956,15 +1114,14 @@ spmv_ring_kernel(const T* __restrict__ vals, const I* __restrict__ cols, const I
             if (++s == stages) { s = 0; parity ^= 1u; }
         }
     }
-    if (dist) {
+    if constexpr (DIST) {
         // the CTA that finishes last closes the epoch and re-arms the arrival counters for the next launch
         __syncthreads();
         if (tid == 0) {
             __threadfence();
-            if (atomicAdd(halo->ctr + 1, 1u) == gridDim.x - 1) {
-                halo->ctr[0] = 0u;
-                halo->ctr[1] = 0u;
-                *halo->epoch = epoch;
+            if (atomicAdd(halo.ctr + 1, 1u) == gridDim.x - 1) {
+                halo.ctr[1] = 0u;
+                *halo.epoch = epoch;
             }
         }
     }
@@ -1306,10 +1463,15 @@ static smb200_status plan_build_range_auto(smb200_crs* m, SpmvPlan& p, int want_
         SMB_TRY(plan_build_range_impl(m, p, SMB200_SPMV_RING, want_lanes, flags, rb, re));
         if (p.variant == SMB200_SPMV_RING && p.n_xwin * 10 >= p.n_blocks * 8) return SMB200_OK;
     }
-    // EXPERIMENTAL, opt-in: x far larger than L2 and long/irregular rows (the ring was not kept) -> column bands
-    if (want == SMB200_SPMV_AUTO && env_int("SMB200_BANDSPLIT_AUTO", 0) != 0 && rb == 0 && re == m->n_rows && m->x_extra == 0 &&
-        m->n_cols * vsize(m->vt) > 2 * (uint64_t)m->ctx->l2_bytes && m->nnz >= 4 * m->n_rows)
-        return plan_build_range_impl(m, p, SMB200_SPMV_BANDSPLIT, want_lanes, flags, rb, re);
+    // x far larger than L2 and no column locality (the ring was not kept): column bands (bandsplit.cu).  The plan holds a
+    // second copy of the matrix (12 instead of 16 bytes per f64/u64 entry), so it is only taken when that fits comfortably.
+    if (want == SMB200_SPMV_AUTO && env_int("SMB200_BANDSPLIT_AUTO", 1) != 0 && rb == 0 && re == m->n_rows && m->x_extra == 0 &&
+        m->n_cols * vsize(m->vt) > 2 * (uint64_t)m->ctx->l2_bytes && m->nnz >= 4 * m->n_rows) {
+        size_t free_b = 0, total_b = 0;
+        const uint64_t need = m->nnz * (vsize(m->vt) + 4) + 16 * (m->n_rows + 1) * 4;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && (uint64_t)free_b > 2 * need)
+            return plan_build_range_impl(m, p, SMB200_SPMV_BANDSPLIT, want_lanes, flags, rb, re);
+    }
     return plan_build_range_impl(m, p, want_variant, want_lanes, flags, rb, re);
 }
 
@@ -1613,7 +1775,7 @@ static smb200_status launch_typed(smb200_crs* m, const SpmvPlan& p, uint64_t rb,
         const int carve = env_int("SMB200_CARVEOUT", -1);
         if (p.variant == SMB200_SPMV_STREAM) {
             const size_t smem = (size_t)(sh.cap + 8) * sizeof(T);
-            auto kern = spmv_stream_kernel<T, I, DOT>;
+            auto kern = g_spmv_band ? spmv_band_kernel<T, I, DOT> : spmv_stream_kernel<T, I, DOT>;
             if (smem > 32 * 1024) SMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             if (carve >= 0) SMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
             kern<<<(unsigned)p.n_blocks, kSpmvThreads, smem, st>>>(vals, cols, offs, (const I*)p.blk_rows, (const I*)p.blk_nnz, sh.cap, xx, yy, dot,
@@ -1637,10 +1799,14 @@ static smb200_status launch_typed(smb200_crs* m, const SpmvPlan& p, uint64_t rb,
             if ((stage * stages + 3072) * ctas > 227u * 1024u) ctas = 1;
             const size_t smem = stage * stages;
             SMB_REQUIRE(smem <= 224u * 1024u, SMB200_ERR_INVALID, "spmv: ring stage of %zu bytes does not fit shared memory", stage);
-            auto kern = spmv_ring_kernel<T, I, DOT>;
-            SMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+
+            auto kern = spmv_ring_kernel<T, I, DOT, false>;
+            auto kern_d = spmv_ring_kernel<T, I, DOT, true>;
+            if (g_halo.host) SMB_CUDA(cudaFuncSetAttribute(kern_d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            else SMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             int resident = 0;
-            SMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, kRingThreads, smem));
+            if (g_halo.host) SMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern_d, kRingThreads, smem));
+            else SMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, kRingThreads, smem));
             if (resident < 1) resident = 1;
             if (resident > ctas) resident = ctas;
             int sms = ctx->sm_count - g_ring_reserve_sms;
@@ -1649,11 +1815,18 @@ static smb200_status launch_typed(smb200_crs* m, const SpmvPlan& p, uint64_t rb,
             if (grid > p.n_blocks) grid = p.n_blocks;
             if (g_ring_grid_cap > 0 && grid > (uint64_t)g_ring_grid_cap) grid = (uint64_t)g_ring_grid_cap;
             g_last_pipe_grid = (unsigned)grid;
-            kern<<<(unsigned)grid, kRingThreads, smem, st>>>(vals, cols, offs, (const I*)p.blk_rows, (const I*)p.blk_nnz, p.seg_lo, p.seg_len,
-                                                           (unsigned)p.n_blocks, sh.cap, p.ocap, xcap, colb, (unsigned)stages, xwin_ok,
-                                                           xwin_ok ? p.lcols : nullptr, (unsigned long long)p.lcols_base, p.loffs,
-                                                           (unsigned long long)p.loffs_row_begin, xx, yy, dot, g_halo.dev,
-                                                           g_halo.dev ? (unsigned)(g_halo.rot % p.n_blocks) : 0u);
+            if (g_halo.host) {
+                kern_d<<<(unsigned)grid, kRingThreads, smem, st>>>(vals, cols, offs, (const I*)p.blk_rows, (const I*)p.blk_nnz, p.seg_lo, p.seg_len,
+                                                                 (unsigned)p.n_blocks, sh.cap, p.ocap, xcap, colb, (unsigned)stages, xwin_ok,
+                                                                 xwin_ok ? p.lcols : nullptr, (unsigned long long)p.lcols_base, p.loffs,
+                                                                 (unsigned long long)p.loffs_row_begin, xx, yy, dot, *g_halo.host,
+                                                                 (unsigned)(g_halo.rot % p.n_blocks));
+            } else {
+                kern<<<(unsigned)grid, kRingThreads, smem, st>>>(vals, cols, offs, (const I*)p.blk_rows, (const I*)p.blk_nnz, p.seg_lo, p.seg_len,
+                                                               (unsigned)p.n_blocks, sh.cap, p.ocap, xcap, colb, (unsigned)stages, xwin_ok,
+                                                               xwin_ok ? p.lcols : nullptr, (unsigned long long)p.lcols_base, p.loffs,
+                                                               (unsigned long long)p.loffs_row_begin, xx, yy, dot, NoHalo(), 0u);
+            }
         } else if (p.variant == SMB200_SPMV_STREAM_PIPE) {
             int stages = env_int("SMB200_PIPE_STAGES", 3);
             if (stages < 3) stages = 3;     // the kernel reads the descriptor of block i + 1 during iteration i
@@ -1752,9 +1925,11 @@ static smb200_status spmv_launch_impl(smb200_crs* m, const SpmvPlan& p, uint64_t
             smb200_crs* part = p.parts[b];
             const bool last = b + 1 == p.parts.size();
             g_spmv_accumulate = b > 0;
+            g_spmv_band = env_int("SMB200_BAND_KERNEL", 1) != 0;
             const smb200_status st = spmv_launch_impl(part, part->plan, 0, part->n_rows, (const char*)x + b * (size_t)p.band_width * es, y,
                                                       last ? w : nullptr, result, last ? roll_dst : nullptr, roll_src, done);
             g_spmv_accumulate = false;
+            g_spmv_band = false;
             SMB_TRY(st);
         }
         return SMB200_OK;

@@ -343,6 +343,12 @@ def test_bandsplit_column_bands(smb, orc, ctx, vdt, idt):
             err = np.abs(got.astype(np.float64) - want.astype(np.float64)) / scale
             assert np.all(np.isfinite(got)) and float(err.max(initial=0.0)) <= tol, (width, float(err.max(initial=0.0)))
             assert np.array_equal(a.mvp(xd).to_numpy(), got)                               # deterministic
+            if vals.size:
+                # scale() reaches the band parts' copies of the values (sparsemat_crs.rs:153-157): exactly 2x (a power of two)
+                a.scale(2.0)
+                assert np.array_equal(a.mvp(xd).to_numpy(), got * vdt(2.0)), "scale() did not reach the band-split plan"
+                a.scale(0.5)
+                assert np.array_equal(a.mvp(xd).to_numpy(), got)
             lhs = np.random.default_rng(8).uniform(-1, 1, n_rows).astype(vdt)
             bil = float(a.inner_prod(smb.DenseVec.from_vec(ctx, lhs), xd))
             ref = float(np.sum(lhs.astype(np.float64) * want.astype(np.float64)))
