@@ -70,13 +70,13 @@ typedef enum {
                                 when the matrix has longer rows.  AUTO picks it when >= 80 % of the blocks
                                 have windows                                                           */
     SMB200_SPMV_BANDSPLIT = 8 /* x larger than L2, scattered columns (power-law / graph matrices): at plan time the
-                                matrix is cut into column bands of about half an L2 of x each (same rows, storage
-                                order kept inside a band, columns rebased to the band -> u32); one STREAM launch
+                                matrix is cut into the fewest equal column bands of at most 0.53 L2 of x (same rows,
+                                storage order kept inside a band, columns rebased to the band -> u32); one launch
                                 per band, the first writes y, the others add to it, so the gathers of a launch
                                 hit a cache-resident band.  Rows are summed band-major: tolerance-exact, not
                                 bit-exact.  Whole-matrix products only (row ranges fall back to STREAM).
-                                EXPERIMENTAL in this round: opt-in, AUTO picks it only under
-                                SMB200_BANDSPLIT_AUTO=1                                                   */
+                                AUTO picks it when x is more than twice the L2, the ring kernel was not kept and
+                                the plan's second copy of the matrix fits (SMB200_BANDSPLIT_AUTO=0 disables)      */
 } smb200_spmv_variant;
 
 /* flags for smb200_crs_configure */
@@ -208,12 +208,15 @@ smb200_status smb200_crs_free(smb200_crs* m);
  * offset_rows[n_rows+1], columns[nnz], values[nnz] exactly as SparseMatCRS holds them (sparsemat_crs.rs:9-17), each
  * zero-padded to 8 bytes; little endian.  ERR_IO on open/read/write failures, foreign or truncated files and checksum
  * mismatches.  crsfile_* are host-only (no device needed): info fills vt, it and out3 = {n_rows, n_cols, nnz} so the
- * caller can size the buffers for crsfile_read.  crs_save downloads and writes; crs_load reads and uploads (with the
- * validation of smb200_crs_upload). */
+ * caller can size the buffers for crsfile_read, which takes their capacities in bytes and refuses (ERR_INVALID) a file
+ * that needs more — the file may have changed in between.  The header's sizes are checked against the file's size
+ * before anything is allocated or read.  crs_save downloads and writes; crs_load reads (one open) and uploads (with
+ * the validation of smb200_crs_upload). */
 smb200_status smb200_crsfile_write(const char* path, smb200_vtype vt, smb200_itype it, uint64_t n_rows, uint64_t n_cols,
                                    uint64_t nnz, const void* values, const void* columns, const void* offset_rows);
 smb200_status smb200_crsfile_info(const char* path, int32_t* vt, int32_t* it, uint64_t* out3);
-smb200_status smb200_crsfile_read(const char* path, void* values, void* columns, void* offset_rows);
+smb200_status smb200_crsfile_read(const char* path, void* values, uint64_t values_cap_bytes, void* columns,
+                                  uint64_t columns_cap_bytes, void* offset_rows, uint64_t offsets_cap_bytes);
 smb200_status smb200_crs_save(const smb200_crs* m, const char* path);
 smb200_status smb200_crs_load(smb200_ctx* ctx, const char* path, smb200_crs** out);
 /* out3 = {n_rows, n_cols, n_non_zero_entries} (sparsemat_crs.rs:124-134). */
@@ -243,6 +246,12 @@ smb200_status smb200_spmv(smb200_crs* a, const smb200_vec* x, smb200_vec* y);
 /* Same through host buffers (pinned or pageable): H2D x, SpMV, D2H y, synchronised — the call the
  * `Mul<DenseVec<T>>` operator (sparsematrix.rs:435-443) maps to when the vectors live on the host. */
 smb200_status smb200_spmv_host(smb200_crs* a, const void* x_host, uint64_t nx, void* y_host);
+/* SparseMatrix::transpose (sparsematrix.rs:174-183) on the device: row j of the result holds the entries of column j
+ * ordered by source row (the order `ret.set(col, i, val)` appends them in on the assembly format, then `to_crs()`);
+ * n_rows = largest column + 1, n_cols = last non-empty row + 1, 0 x 0 without entries.  Bit-exact (integer / copy
+ * work: a stable radix sort of the entries by column).  A duplicate (i, j) — which the reference's assembly cannot
+ * produce — stays two entries. */
+smb200_status smb200_crs_transpose(const smb200_crs* a, smb200_crs** out);
 /* SparseMatrix::inner_prod (sparsematrix.rs:161-171): lhs^T A rhs in one pass. */
 smb200_status smb200_bilinear(smb200_crs* a, const smb200_vec* lhs, const smb200_vec* rhs, double* out);
 

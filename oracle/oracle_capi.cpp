@@ -230,6 +230,8 @@ ORC_VEC(double, f64)
         out3[0] = m->n_rows(); out3[1] = m->n_cols(); out3[2] = m->nnz(); }                                         \
     void orc_il_export_##S(void* h, I* columns, T* values, I* pos_start, I* next) {                                 \
         il_export(static_cast<SparseMatIndexList<T, I>*>(h), columns, values, pos_start, next); }                   \
+    void* orc_il_transpose_##S(void* h) {                                                                           \
+        return new SparseMatIndexList<T, I>(transpose(*static_cast<SparseMatIndexList<T, I>*>(h))); }               \
     void* orc_il_to_crs_##S(void* h) {                                                                              \
         return new SparseMatCRS<T, I>(SparseMatCRS<T, I>::from_indexlist(*static_cast<SparseMatIndexList<T, I>*>(h))); } \
     void orc_crs_free_##S(void* h) { delete static_cast<SparseMatCRS<T, I>*>(h); }                                  \

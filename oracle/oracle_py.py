@@ -237,6 +237,15 @@ class IndexListMat:
         fn("orc_il_export", self.sfx)(self.h, _p(columns), _p(values), _p(pos_start), _p(nxt))
         return columns, values, pos_start, nxt
 
+    def transpose(self) -> "IndexListMat":
+        """SparseMatrix::transpose (sparsematrix.rs:174-183) on the assembly format."""
+        f = fn("orc_il_transpose", self.sfx)
+        f.restype = C.c_void_p
+        t = IndexListMat.__new__(IndexListMat)
+        t.vdt, t.idt, t.sfx = self.vdt, self.idt, self.sfx
+        t.h = C.c_void_p(f(self.h))
+        return t
+
     def to_crs(self):
         """(n_rows, n_cols, values, columns, offset_rows) exactly as from_sparsemat_index lays them out."""
         f = fn("orc_il_to_crs", self.sfx)

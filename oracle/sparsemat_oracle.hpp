@@ -275,6 +275,17 @@ struct SparseMatIndexList {
     }
 };
 
+// sparsematrix.rs:174-183 — `transpose`: ret = with_capacity(nnz); rows ascending, a row's entries in storage order,
+// ret.set(col, i, val).  Restated on the assembly format (the CRS `push` path of the reference is O(nnz) per insert and
+// loses rows through its first-insert quirk, sparsemat_crs.rs:71-92, so nobody transposes through it).
+template <class T, class I>
+SparseMatIndexList<T, I> transpose(const SparseMatIndexList<T, I>& a) {
+    SparseMatIndexList<T, I> ret;
+    for (std::size_t i = 0; i < a.n_rows(); ++i)
+        a.for_row(i, [&](I c, T v) { ret.set(static_cast<std::size_t>(c), i, v); return true; });
+    return ret;
+}
+
 // ------------------------------------------------------------------------------------------------
 // sparsemat_crs.rs:9-223 — the compute format.
 template <class T, class I>

@@ -9,10 +9,13 @@ fn main() {
     let csrc = root.join("sparsemat_b200/csrc");
     let out = PathBuf::from(env::var("OUT_DIR").unwrap());
     let nvcc = env::var("NVCC").unwrap_or_else(|_| "nvcc".into());
-    let sources = ["context.cu", "vector_ops.cu", "crs.cu", "generators.cu", "spmv.cu", "cg.cu", "dist.cu", "partition.cpp"];
+    // the same translation units as sparsemat_b200/csrc/Makefile (SRCS_CU, SRCS_CPP, SRCS_HOST); tests/test_abi_and_host.py
+    // fails when the two lists drift apart
+    let sources = ["context.cu", "vector_ops.cu", "crs.cu", "generators.cu", "spmv.cu", "bandsplit.cu", "cg.cu", "pcg.cu", "dist.cu",
+                   "transpose.cu", "partition.cpp", "crs_io.cpp", "../host/assembler_capi.cpp"];
     let mut objects = Vec::new();
     for s in sources.iter() {
-        let obj = out.join(format!("{}.o", s));
+        let obj = out.join(format!("{}.o", s.replace("../", "").replace("/", "_")));
         let st = Command::new(&nvcc)
             .args(&["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "--expt-relaxed-constexpr",
                     "-Xcompiler", "-fPIC", "-c"])

@@ -155,6 +155,11 @@ impl<T: GpuValue, I: GpuIndex> GpuCrs<T, I> {
         check(unsafe { sys::smb200_spmv_host(self.h, x.as_ptr() as *const c_void, x.len() as u64, y.as_mut_ptr() as *mut c_void) });
         V::from_vec(y)
     }
+    pub fn transpose(&self) -> Self {                                                                   // sparsematrix.rs:174-183
+        let mut h = std::ptr::null_mut();
+        check(unsafe { sys::smb200_crs_transpose(self.h, &mut h) });
+        GpuCrs { h, ctx: self.ctx.clone(), _t: PhantomData }
+    }
     pub fn inner_prod(&self, lhs: &DeviceVec<T>, rhs: &DeviceVec<T>) -> T {                             // sparsematrix.rs:161-171
         let mut out = 0.0;
         check(unsafe { sys::smb200_bilinear(self.h, lhs.h, rhs.h, &mut out) });

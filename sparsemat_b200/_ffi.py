@@ -108,7 +108,7 @@ PROTOTYPES = {
     "smb200_crs_free": (_i32, [_p]),
     "smb200_crsfile_write": (_i32, [C.c_char_p, _i32, _i32, _u64, _u64, _u64, _p, _p, _p]),
     "smb200_crsfile_info": (_i32, [C.c_char_p, C.POINTER(_i32), C.POINTER(_i32), _u64p]),
-    "smb200_crsfile_read": (_i32, [C.c_char_p, _p, _p, _p]),
+    "smb200_crsfile_read": (_i32, [C.c_char_p, _p, _u64, _p, _u64, _p, _u64]),
     "smb200_crs_save": (_i32, [_p, C.c_char_p]),
     "smb200_crs_load": (_i32, [_p, C.c_char_p, _pp]),
     "smb200_crs_dims": (_i32, [_p, _u64p]),
@@ -121,6 +121,7 @@ PROTOTYPES = {
     "smb200_gen_powerlaw": (_i32, [_p, _i32, _i32, _u64, _u64, _u64, _u64, _u64, _u64, _pp]),
     "smb200_spmv": (_i32, [_p, _p, _p]),
     "smb200_spmv_host": (_i32, [_p, _p, _u64, _p]),
+    "smb200_crs_transpose": (_i32, [_p, _pp]),
     "smb200_bilinear": (_i32, [_p, _p, _p, _dp]),
     "smb200_cg_solve": (_i32, [_p, _p, _p, C.c_double, _i32, _u64, C.POINTER(CgStats)]),
     "smb200_cg_history": (_i32, [_p, _dp, _u64, _u64p]),

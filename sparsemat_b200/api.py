@@ -248,11 +248,22 @@ class DenseVec:
 
 
 # --------------------------------------------------------------------------------------------------------------
+def _check_crs_lengths(n_rows, values, columns, offset_rows) -> None:
+    """The reference derives these lengths from its Vecs (sparsemat_crs.rs:9-17) and cannot get them wrong; raw arrays can,
+    and a short array would be read past its end by the upload."""
+    if columns.size != values.size:
+        raise ValueError(f"columns has {columns.size} entries, values has {values.size}")
+    want = n_rows + 1 if (n_rows or values.size) else offset_rows.size
+    if offset_rows.size != want:
+        raise ValueError(f"offset_rows has {offset_rows.size} entries, expected n_rows + 1 = {want}")
+
+
 def crsfile_write(path, n_rows, n_cols, values, columns, offset_rows) -> None:
     """Host only: write CRS arrays (sparsemat_crs.rs:9-17 layout) as a binary container.  No device needed."""
     values = np.ascontiguousarray(values)
     columns = np.ascontiguousarray(columns)
     offset_rows = np.ascontiguousarray(offset_rows, columns.dtype)
+    _check_crs_lengths(n_rows, values, columns, offset_rows)
     check(lib.smb200_crsfile_write(os.fsencode(path), F.vtype_of(values.dtype), F.itype_of(columns.dtype), n_rows, n_cols,
                                    values.size, F.ptr(values) if values.size else None, F.ptr(columns) if columns.size else None,
                                    F.ptr(offset_rows) if n_rows else None))
@@ -267,8 +278,9 @@ def crsfile_read(path):
     values = np.empty(d[2], F.VDTYPES[vt.value])
     columns = np.empty(d[2], F.IDTYPES[it.value])
     offsets = np.empty(d[0] + 1 if d[0] else 0, F.IDTYPES[it.value])
-    check(lib.smb200_crsfile_read(os.fsencode(path), F.ptr(values) if values.size else None, F.ptr(columns) if columns.size else None,
-                                  F.ptr(offsets) if offsets.size else None))
+    check(lib.smb200_crsfile_read(os.fsencode(path), F.ptr(values) if values.size else None, values.nbytes,
+                                  F.ptr(columns) if columns.size else None, columns.nbytes,
+                                  F.ptr(offsets) if offsets.size else None, offsets.nbytes))
     return int(d[0]), int(d[1]), values, columns, offsets
 
 
@@ -297,6 +309,7 @@ class SparseMatCRS:
         values = np.ascontiguousarray(values)
         columns = np.ascontiguousarray(columns)
         offset_rows = np.ascontiguousarray(offset_rows, columns.dtype)
+        _check_crs_lengths(n_rows, values, columns, offset_rows)
         h = C.c_void_p()
         check(lib.smb200_crs_upload(ctx._h, F.vtype_of(values.dtype), F.itype_of(columns.dtype), n_rows, n_cols,
                                     values.size, F.ptr(values), F.ptr(columns), F.ptr(offset_rows), C.byref(h)))
@@ -399,6 +412,11 @@ class SparseMatCRS:
             y = np.empty(self.n_rows(), self.dtype)
         check(lib.smb200_spmv_host(self._h, F.ptr(x), x.size, F.ptr(y)))
         return y
+
+    def transpose(self) -> "SparseMatCRS":                             # sparsematrix.rs:174-183
+        h = C.c_void_p()
+        check(lib.smb200_crs_transpose(self._h, C.byref(h)))
+        return SparseMatCRS(self.ctx, h)
 
     def inner_prod(self, lhs: DenseVec, rhs: DenseVec):                # sparsematrix.rs:161-171
         out = C.c_double()

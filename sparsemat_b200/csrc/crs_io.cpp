@@ -18,6 +18,8 @@
 //                 values[nnz]             (value type), zero-padded to 8
 #include "common.cuh"
 
+#include <sys/stat.h>
+
 #include <cerrno>
 #include <cstdio>
 #include <memory>
@@ -65,8 +67,20 @@ smb200_status read_header(FILE* f, const char* path, Header* h) {
     // sizes a 64-bit byte count can hold, and an index type that can hold them (offset_rows is Vec<I>)
     SMB_REQUIRE(h->nnz < (1ull << 59) && h->n_rows < (1ull << 59), SMB200_ERR_IO, "crsfile: %s: implausible dimensions", path);
     SMB_REQUIRE(h->it == SMB200_U64 || h->nnz <= 0xFFFFFFFFull, SMB200_ERR_IO, "crsfile: %s: nnz does not fit the u32 offsets", path);
+    // the sizes the header claims must be the sizes the file has: nothing is allocated or read on the word of a corrupt header
+    struct stat sb;
+    SMB_REQUIRE(fstat(fileno(f), &sb) == 0, SMB200_ERR_IO, "crsfile: cannot stat %s: %s", path, strerror(errno));
+    auto padded = [](uint64_t n) { return (n + 7) & ~(uint64_t)7; };
+    const uint64_t is = h->it == SMB200_U64 ? 8 : 4, vs = h->vt == SMB200_F64 ? 8 : 4;
+    const uint64_t want = kHeaderBytes + (h->n_rows ? padded((h->n_rows + 1) * is) : 0) + padded(h->nnz * is) + padded(h->nnz * vs);
+    SMB_REQUIRE((uint64_t)sb.st_size == want, SMB200_ERR_IO, "crsfile: %s holds %llu bytes, its header describes %llu (truncated or corrupt)",
+                path, (unsigned long long)sb.st_size, (unsigned long long)want);
     return SMB200_OK;
 }
+
+// Body of an opened file whose header was parsed and checked against the file size; capacities in bytes.
+smb200_status read_body(FILE* f, const char* path, const Header& h, void* values, uint64_t values_cap, void* columns,
+                        uint64_t columns_cap, void* offset_rows, uint64_t offsets_cap);
 
 smb200_status write_block(FILE* f, const char* path, const void* data, size_t n, uint64_t* sum) {
     static const unsigned char zeros[8] = {0};
@@ -87,6 +101,24 @@ smb200_status read_block(FILE* f, const char* path, void* data, size_t n, uint64
     }
     const size_t p = pad8(n);
     if (p) SMB_REQUIRE(fread(skip, 1, p, f) == p, SMB200_ERR_IO, "crsfile: %s is truncated", path);
+    return SMB200_OK;
+}
+
+smb200_status read_body(FILE* f, const char* path, const Header& h, void* values, uint64_t values_cap, void* columns,
+                        uint64_t columns_cap, void* offset_rows, uint64_t offsets_cap) {
+    const uint64_t ob = h.n_rows ? (h.n_rows + 1) * isize((int)h.it) : 0, cb = h.nnz * isize((int)h.it), vb = h.nnz * vsize((int)h.vt);
+    SMB_REQUIRE((values && columns) || h.nnz == 0, SMB200_ERR_INVALID, "crsfile_read: NULL values/columns");
+    SMB_REQUIRE(offset_rows || h.n_rows == 0, SMB200_ERR_INVALID, "crsfile_read: NULL offset_rows");
+    SMB_REQUIRE(values_cap >= vb && columns_cap >= cb && offsets_cap >= ob, SMB200_ERR_INVALID,
+                "crsfile_read: %s needs %llu / %llu / %llu bytes (values / columns / offset_rows), the buffers hold %llu / %llu / %llu",
+                path, (unsigned long long)vb, (unsigned long long)cb, (unsigned long long)ob, (unsigned long long)values_cap,
+                (unsigned long long)columns_cap, (unsigned long long)offsets_cap);
+    uint64_t sum = kFnvBasis;
+    if (h.n_rows) SMB_TRY(read_block(f, path, offset_rows, (size_t)ob, &sum));
+    SMB_TRY(read_block(f, path, columns, (size_t)cb, &sum));
+    SMB_TRY(read_block(f, path, values, (size_t)vb, &sum));
+    SMB_REQUIRE(sum == h.checksum, SMB200_ERR_IO, "crsfile_read: %s: checksum mismatch (file %016llx, data %016llx)", path,
+                (unsigned long long)h.checksum, (unsigned long long)sum);
     return SMB200_OK;
 }
 
@@ -141,21 +173,15 @@ smb200_status smb200_crsfile_info(const char* path, int32_t* vt, int32_t* it, ui
     return SMB200_OK;
 }
 
-smb200_status smb200_crsfile_read(const char* path, void* values, void* columns, void* offset_rows) {
+smb200_status smb200_crsfile_read(const char* path, void* values, uint64_t values_cap_bytes, void* columns,
+                                  uint64_t columns_cap_bytes, void* offset_rows, uint64_t offsets_cap_bytes) {
     SMB_REQUIRE(path, SMB200_ERR_INVALID, "crsfile_read: NULL path");
     File f(fopen(path, "rb"));
     SMB_REQUIRE(f, SMB200_ERR_IO, "crsfile_read: cannot open %s: %s", path, strerror(errno));
     Header h;
     SMB_TRY(read_header(f.get(), path, &h));
-    SMB_REQUIRE((values && columns) || h.nnz == 0, SMB200_ERR_INVALID, "crsfile_read: NULL values/columns");
-    SMB_REQUIRE(offset_rows || h.n_rows == 0, SMB200_ERR_INVALID, "crsfile_read: NULL offset_rows");
-    uint64_t sum = kFnvBasis;
-    if (h.n_rows) SMB_TRY(read_block(f.get(), path, offset_rows, (size_t)(h.n_rows + 1) * isize((int)h.it), &sum));
-    SMB_TRY(read_block(f.get(), path, columns, (size_t)h.nnz * isize((int)h.it), &sum));
-    SMB_TRY(read_block(f.get(), path, values, (size_t)h.nnz * vsize((int)h.vt), &sum));
-    SMB_REQUIRE(sum == h.checksum, SMB200_ERR_IO, "crsfile_read: %s: checksum mismatch (file %016llx, data %016llx)", path,
-                (unsigned long long)h.checksum, (unsigned long long)sum);
-    return SMB200_OK;
+    // the file may have changed since the caller sized its buffers with crsfile_info: the capacities decide
+    return read_body(f.get(), path, h, values, values_cap_bytes, columns, columns_cap_bytes, offset_rows, offsets_cap_bytes);
 }
 
 smb200_status smb200_crs_save(const smb200_crs* m, const char* path) {
@@ -170,15 +196,23 @@ smb200_status smb200_crs_save(const smb200_crs* m, const char* path) {
 
 smb200_status smb200_crs_load(smb200_ctx* ctx, const char* path, smb200_crs** out) {
     SMB_REQUIRE(ctx && path && out, SMB200_ERR_INVALID, "crs_load: NULL argument");
-    int32_t vt = 0, it = 0;
-    uint64_t d[3] = {0, 0, 0};
-    SMB_TRY(smb200_crsfile_info(path, &vt, &it, d));
-    std::vector<unsigned char> values((size_t)d[2] * vsize(vt)), columns((size_t)d[2] * isize(it)),
-        offsets(d[0] ? (size_t)(d[0] + 1) * isize(it) : 0);
-    SMB_TRY(smb200_crsfile_read(path, values.data(), columns.data(), offsets.data()));
+    // one open: the header that sizes the buffers is the header whose body is read into them
+    File f(fopen(path, "rb"));
+    SMB_REQUIRE(f, SMB200_ERR_IO, "crs_load: cannot open %s: %s", path, strerror(errno));
+    Header h;
+    SMB_TRY(read_header(f.get(), path, &h));
+    std::vector<unsigned char> values, columns, offsets;
+    try {
+        values.resize((size_t)h.nnz * vsize((int)h.vt));
+        columns.resize((size_t)h.nnz * isize((int)h.it));
+        offsets.resize(h.n_rows ? (size_t)(h.n_rows + 1) * isize((int)h.it) : 0);
+    } catch (const std::exception& e) {
+        SMB_FAIL(SMB200_ERR_OOM, "crs_load: %s: cannot hold %llu entries in host memory (%s)", path, (unsigned long long)h.nnz, e.what());
+    }
+    SMB_TRY(read_body(f.get(), path, h, values.data(), values.size(), columns.data(), columns.size(), offsets.data(), offsets.size()));
     // the upload validates the arrays (monotone offsets ending at nnz, columns < n_cols) like any other matrix
-    return smb200_crs_upload(ctx, (smb200_vtype)vt, (smb200_itype)it, d[0], d[1], d[2], values.data(), columns.data(),
-                             d[0] ? offsets.data() : nullptr, out);
+    return smb200_crs_upload(ctx, (smb200_vtype)h.vt, (smb200_itype)h.it, h.n_rows, h.n_cols, h.nnz, values.data(), columns.data(),
+                             h.n_rows ? offsets.data() : nullptr, out);
 }
 
 }  // extern "C"

@@ -125,10 +125,20 @@ public:
     // Equivalent of the overlay's `SparseMatCRS::raw_parts()` hand-over: finished arrays in.
     static SparseMatCRS from_raw_parts(const Context& ctx, uint64_t n_rows, uint64_t n_cols, const std::vector<T>& values,
                                        const std::vector<I>& columns, const std::vector<I>& offset_rows) {
+        // the reference derives these lengths from its Vecs and cannot get them wrong; raw arrays can
+        if (columns.size() != values.size()) throw Panic("SparseMatCRS::from_raw_parts: columns and values differ in length");
+        if (offset_rows.size() != (n_rows || !values.empty() ? n_rows + 1 : offset_rows.size()))
+            throw Panic("SparseMatCRS::from_raw_parts: offset_rows must hold n_rows + 1 entries");
         smb200_crs* m = nullptr;
         check(smb200_crs_upload(ctx.get(), vtype_of<T>(), itype_of<I>(), n_rows, n_cols, values.size(), values.data(),
                                 columns.data(), offset_rows.data(), &m));
         return SparseMatCRS(ctx, m);
+    }
+    // sparsematrix.rs:174-183 — row j of the result: column j's entries ordered by source row
+    SparseMatCRS transpose() const {
+        smb200_crs* m = nullptr;
+        check(smb200_crs_transpose(raw(), &m));
+        return SparseMatCRS(ctx_, m);
     }
     // Binary CRS container (additive: the reference has text/PBM writers only, sparsematrix.rs:304-338): the three arrays
     // byte for byte behind a checksummed header.  load() refuses files of another value/index type.

@@ -201,10 +201,71 @@ def test_binary_crs_container_round_trip_and_damage(tmp_path):
 
     refused(b"NOTACRS!" + good[8:], "not a SMBCRS01 file")
     refused(good[:40], "shorter than a header")
-    refused(good[:-9], "truncated")
+    refused(good[:-9], "truncated or corrupt")
     flipped = bytearray(good)
     flipped[-13] ^= 0x10                                                      # one bit inside the values (the last 4 bytes are padding)
     refused(bytes(flipped), "checksum mismatch")
+    # a header that claims 2^31 entries (24 GB): refused on the file's size, before anything is allocated on its word
+    huge = bytearray(good)
+    huge[32:40] = (1 << 31).to_bytes(8, "little")
+    refused(bytes(huge), "truncated or corrupt")
+    refused(good + b"\0" * 8, "truncated or corrupt")                        # trailing bytes the header does not describe
     with pytest.raises(smb.SmbError) as e:
         smb.crsfile_read(tmp_path / "does_not_exist.smbcrs")
     assert e.value.status == F.ERR_IO
+    # buffers smaller than the file needs are refused (the capacities are part of the call)
+    vt, it = C.c_int32(), C.c_int32()
+    d = (C.c_uint64 * 3)()
+    gp = os.fsencode(tmp_path / "m0_37.smbcrs")
+    assert F.lib.smb200_crsfile_info(gp, C.byref(vt), C.byref(it), d) == F.OK
+    v = np.empty(int(d[2]), np.float32); c = np.empty(int(d[2]), np.uint32); o = np.empty(int(d[0]) + 1, np.uint32)
+    assert F.lib.smb200_crsfile_read(gp, F.ptr(v), v.nbytes, F.ptr(c), c.nbytes, F.ptr(o), o.nbytes) == F.OK
+    assert F.lib.smb200_crsfile_read(gp, F.ptr(v), v.nbytes - 4, F.ptr(c), c.nbytes, F.ptr(o), o.nbytes) == F.ERR_INVALID
+
+
+def test_rust_build_script_compiles_the_same_sources_as_the_makefile():
+    """rust/sparsemat-b200-sys/build.rs (the `build.rs invoking nvcc` of the north star) and csrc/Makefile must list the same
+    translation units: a stale list links a library with missing symbols."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    mk = open(os.path.join(root, "sparsemat_b200", "csrc", "Makefile")).read()
+    srcs = set()
+    for var in ("SRCS_CU", "SRCS_CPP", "SRCS_HOST"):
+        m = re.search(rf"^{var}\s*:=\s*(.*)$", mk, re.M)
+        assert m, var
+        srcs |= set(m.group(1).split())
+    rs = open(os.path.join(root, "rust", "sparsemat-b200-sys", "build.rs")).read()
+    m = re.search(r"let sources = \[(.*?)\];", rs, re.S)
+    assert m
+    rust_srcs = set(re.findall(r'"([^"]+)"', m.group(1)))
+    assert rust_srcs == srcs, (sorted(rust_srcs - srcs), sorted(srcs - rust_srcs))
+    for s_ in srcs:
+        assert os.path.exists(os.path.join(root, "sparsemat_b200", "csrc", s_)), s_
+
+
+def test_rust_sys_crate_declares_exactly_the_header_functions():
+    """rust/sparsemat-b200-sys/src/lib.rs mirrors include/smb200.h one to one (names and argument counts).  smb200_host.h
+    is for language mirrors WITHOUT the reference crate (Python, C): the Rust overlay keeps the crate's own SparseMatIndexList."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+    def c_decls(path):
+        txt = re.sub(r"/\*.*?\*/", "", open(path).read(), flags=re.S)
+        out = {}
+        for m in re.finditer(r"\b(smb200_\w+)\s*\(([^;{]*?)\)\s*;", txt, re.S):
+            args = m.group(2).strip()
+            out[m.group(1)] = 0 if args in ("", "void") else args.count(",") + 1
+        return out
+
+    hdr = {}
+    hdr.update(c_decls(os.path.join(root, "include", "smb200.h")))
+    rs = open(os.path.join(root, "rust", "sparsemat-b200-sys", "src", "lib.rs")).read()
+    rust = {}
+    for m in re.finditer(r"pub fn (smb200_\w+)\s*\(([^)]*)\)", rs, re.S):
+        args = m.group(2).strip()
+        rust[m.group(1)] = 0 if not args else args.count(":")
+    missing = sorted(set(hdr) - set(rust))
+    extra = sorted(set(rust) - set(hdr))
+    assert not missing and not extra, {"not bound in the sys crate": missing, "bound but not declared": extra}
+    wrong = {k: (hdr[k], rust[k]) for k in hdr if hdr[k] != rust[k]}
+    assert not wrong, wrong
