@@ -27,6 +27,7 @@
 #include "halo.cuh"
 #include "reduce.cuh"
 
+#include <algorithm>
 #include <chrono>
 #include <cstdlib>
 
@@ -41,6 +42,7 @@ constexpr unsigned kBlkNoFit = 1u;   // PIPE block flags: slice larger than a st
 constexpr unsigned kBlkLong = 2u;    //                   a row of more than kWarpRowMin entries -> two-pass row sums
 constexpr unsigned kBlkShort = 4u;   //                   every row has <= kRowMajorMax entries -> row-major path
 constexpr int kRowMajorMax = 32;
+constexpr int kRingRowMax = 256;     // RING: longest row it takes (8 lanes per row x 32 entries per lane)
 constexpr int kPipeMaxStages = 8;
 
 struct DotArgs {
@@ -911,21 +913,44 @@ __device__ __forceinline__ double ring_rows(const T* sv, const I* sc, const I* s
 // Same with compressed columns: the plan stored, for every non-zero of a windowed block, the 16-bit position of its
 // column inside the block's concatenated x windows, so a stage carries 2 bytes per column instead of sizeof(I) and the
 // consumer needs no window search.  The arithmetic (operands, order, roundings) is unchanged.
-template <class T, class I, bool DOT, bool O16>
+template <class T, class I, bool DOT, bool O16, int LANES = 1>
 __device__ __forceinline__ double ring_rows_c16(const T* sv, const uint16_t* sc, const I* so, const T* sx, const RingDesc& d,
                                                 unsigned lane_id, unsigned n_lanes, T* __restrict__ y, const T* __restrict__ w) {
     const uint64_t r0 = d.r0, r1 = d.r1, a0 = d.a0, r0a = d.r0a;
     double acc = 0.0;
-    for (uint64_t r = r0 + lane_id; r < r1; r += n_lanes) {
-        unsigned ka, ke;
-        ring_row_span<I, O16>(so, r, r0, r0a, a0, ka, ke);
-        T wv = T(0);
-        if constexpr (DOT) wv = __ldg(w + r);
-        T sum = T(0);
+    if constexpr (LANES > 1) {
+        // Rows of 33..256 entries (FEM with several unknowns per node): LANES consecutive threads share a row, lane l sums the
+        // entries l, l + LANES, ... (consecutive shared-memory words across the group), a fixed xor-shuffle tree adds the
+        // partial sums.  Deterministic, but not the reference's storage order: inside the north-star tolerance, not bit-exact.
+        const unsigned sub = lane_id % LANES, grp = lane_id / LANES, n_grp = n_lanes / LANES;
+        const uint64_t rows = r1 - r0;
+        // every thread of a warp runs the same number of iterations (the shuffles below need the whole group converged)
+        for (uint64_t i = grp; i < ((rows + n_grp - 1) / n_grp) * n_grp; i += n_grp) {
+            const bool live = i < rows;
+            const uint64_t r = r0 + (live ? i : 0);
+            unsigned ka = 0, ke = 0;
+            if (live) ring_row_span<I, O16>(so, r, r0, r0a, a0, ka, ke);
+            T sum = T(0);
+            for (unsigned k = ka + sub; k < ke; k += LANES) sum = add_rn(sum, mul_rn(sx[sc[k]], sv[k]));
+#pragma unroll
+            for (int o = LANES / 2; o > 0; o >>= 1) sum = add_rn(sum, __shfl_xor_sync(0xffffffffu, sum, o));
+            if (live && sub == 0) {
+                y[r] = sum;
+                if constexpr (DOT) acc += (double)mul_rn(__ldg(w + r), sum);
+            }
+        }
+    } else {
+        for (uint64_t r = r0 + lane_id; r < r1; r += n_lanes) {
+            unsigned ka, ke;
+            ring_row_span<I, O16>(so, r, r0, r0a, a0, ka, ke);
+            T wv = T(0);
+            if constexpr (DOT) wv = __ldg(w + r);
+            T sum = T(0);
 #pragma unroll 4
-        for (unsigned k = ka; k < ke; ++k) sum = add_rn(sum, mul_rn(sx[sc[k]], sv[k]));
-        y[r] = sum;
-        if constexpr (DOT) acc += (double)mul_rn(wv, sum);
+            for (unsigned k = ka; k < ke; ++k) sum = add_rn(sum, mul_rn(sx[sc[k]], sv[k]));
+            y[r] = sum;
+            if constexpr (DOT) acc += (double)mul_rn(wv, sum);
+        }
     }
     return acc;
 }
@@ -934,7 +959,8 @@ __device__ __forceinline__ double ring_rows_c16(const T* sv, const uint16_t* sc,
 struct NoHalo {};
 template <bool DIST> struct HaloParam { using type = NoHalo; };
 template <> struct HaloParam<true> { using type = HaloDev; };       // by value: its fields are read from the constant bank
-template <class T, class I, bool DOT, bool DIST>
+// LANES = threads per row of the compressed-column path: 1 (rows <= 32 entries, storage-order sums, bit-exact) or 2 / 4 / 8.
+template <class T, class I, bool DOT, bool DIST, int LANES>
 __global__ void __launch_bounds__(kRingThreads, 2)
 spmv_ring_kernel(const T* __restrict__ vals, const I* __restrict__ cols, const I* __restrict__ offs,
                  const I* __restrict__ blk_rows, const I* __restrict__ blk_nnz, const unsigned long long* __restrict__ seg_lo,
@@ -1097,8 +1123,8 @@ spmv_ring_kernel(const T* __restrict__ vals, const I* __restrict__ cols, const I
             const T* w = (const T*)dot.w;
             if (d.c16) {
                 const uint16_t* sc16 = reinterpret_cast<const uint16_t*>(base + o_cols);
-                if (d.o16) acc += ring_rows_c16<T, I, DOT, true>(sv, sc16, so, sx, d, lane_id, n_lanes, y, w);
-                else acc += ring_rows_c16<T, I, DOT, false>(sv, sc16, so, sx, d, lane_id, n_lanes, y, w);
+                if (d.o16) acc += ring_rows_c16<T, I, DOT, true, LANES>(sv, sc16, so, sx, d, lane_id, n_lanes, y, w);
+                else acc += ring_rows_c16<T, I, DOT, false, LANES>(sv, sc16, so, sx, d, lane_id, n_lanes, y, w);
             } else switch (d.xwin) {              // number of x windows of the block (block-uniform)
                 case 0:
                     if (d.o16) acc += ring_rows<T, I, DOT, 0, true, DIST>(sv, sc, so, sx, d, lane_id, n_lanes, x, y, w, gx, g0);
@@ -1137,8 +1163,9 @@ __global__ void __launch_bounds__(128)
 block_segments_kernel(const I* __restrict__ cols, const I* __restrict__ blk_nnz, unsigned shift, unsigned xcap, unsigned xalign,
                       unsigned long long* __restrict__ seg_lo, unsigned* __restrict__ seg_len, unsigned long long* __restrict__ n_ok) {
     __shared__ unsigned bitmap[kSegWords];
+    constexpr int kMaxRuns = 64;
     __shared__ unsigned long long s_lo[kNSeg], s_hi[kNSeg];
-    __shared__ unsigned run_b0[kNSeg], run_b1[kNSeg];
+    __shared__ unsigned run_b0[kMaxRuns], run_b1[kMaxRuns];
     __shared__ int s_nruns;
     __shared__ unsigned s_bmin, s_bmax;
     const size_t b = blockIdx.x;
@@ -1159,16 +1186,26 @@ block_segments_kernel(const I* __restrict__ cols, const I* __restrict__ blk_nnz,
     if (threadIdx.x == 0 && n1 > n0) {
         int nr = 0;
         unsigned last = 0;
-        for (unsigned wd = s_bmin >> 5; wd <= (s_bmax >> 5) && nr <= kNSeg; ++wd) {
+        for (unsigned wd = s_bmin >> 5; wd <= (s_bmax >> 5) && nr <= kMaxRuns; ++wd) {
             unsigned bits = bitmap[wd];
             while (bits) {
                 const unsigned bk = wd * 32u + (unsigned)(__ffs((int)bits) - 1);
                 bits &= bits - 1u;
                 if (nr > 0 && bk <= last + 2u) run_b1[nr - 1] = bk;            // same run (a one-bucket gap is bridged)
-                else if (nr == kNSeg) { nr = kNSeg + 1; break; }
+                else if (nr == kMaxRuns) { nr = kMaxRuns + 1; break; }
                 else { run_b0[nr] = bk; run_b1[nr] = bk; ++nr; }
                 last = bk;
             }
+        }
+        // more runs than windows (several unknowns per node, wide stencils): close the narrowest gaps first; whether the
+        // merged windows still fit the stage is decided on their exact bounds below
+        while (nr > kNSeg && nr <= kMaxRuns) {
+            int at = 0;
+            unsigned best = 0xffffffffu;
+            for (int i = 0; i + 1 < nr; ++i) { const unsigned gap = run_b0[i + 1] - run_b1[i]; if (gap < best) { best = gap; at = i; } }
+            run_b1[at] = run_b1[at + 1];
+            for (int i = at + 1; i + 1 < nr; ++i) { run_b0[i] = run_b0[i + 1]; run_b1[i] = run_b1[i + 1]; }
+            --nr;
         }
         s_nruns = nr;
     }
@@ -1400,7 +1437,7 @@ static void stream_shape(const smb200_crs* m, int variant, unsigned* cap, unsign
     if (c > kMaxCap) c = kMaxCap;
     t = c - c / 9;                     // leave room for the row that straddles the target
     // rows are short: a block overshoots the target by < one row, and its slice is widened to multiples of 8 elements
-    if (variant == SMB200_SPMV_RING) t = c - (unsigned)kRowMajorMax - 16;
+    if (variant == SMB200_SPMV_RING) t = c - (unsigned)std::min<uint64_t>(std::max<uint64_t>(m->max_row_len, kRowMajorMax), c / 2) - 16;
     t = (unsigned)env_int("SMB200_STREAM_TARGET", (int)t);
     if (t + 8 > c) t = c - 8;
     *cap = c;
@@ -1459,9 +1496,12 @@ static smb200_status plan_build_range_auto(smb200_crs* m, SpmvPlan& p, int want_
                                            uint64_t rb, uint64_t re) {
     int want = want_variant;
     if (want == SMB200_SPMV_AUTO) want = env_int("SMB200_SPMV_VARIANT", SMB200_SPMV_AUTO);
-    if (want == SMB200_SPMV_AUTO && m->max_row_len <= (uint64_t)kRowMajorMax && m->nnz > 0) {
+    if (want == SMB200_SPMV_AUTO && m->max_row_len <= (uint64_t)kRingRowMax && m->nnz > 0) {
         SMB_TRY(plan_build_range_impl(m, p, SMB200_SPMV_RING, want_lanes, flags, rb, re));
-        if (p.variant == SMB200_SPMV_RING && p.n_xwin * 10 >= p.n_blocks * 8) return SMB200_OK;
+        // rows beyond 32 entries are only worth the ring when every block streams 16-bit columns (the multi-lane row sums
+        // exist for that path only)
+        const bool long_rows = m->max_row_len > (uint64_t)kRowMajorMax;
+        if (p.variant == SMB200_SPMV_RING && (long_rows ? (p.colb == 2 && p.n_xwin == p.n_blocks) : p.n_xwin * 10 >= p.n_blocks * 8)) return SMB200_OK;
     }
     // x far larger than L2 and no column locality (the ring was not kept): column bands (bandsplit.cu).  The plan holds a
     // second copy of the matrix (12 instead of 16 bytes per f64/u64 entry), so it is only taken when that fits comfortably.
@@ -1663,7 +1703,7 @@ static smb200_status plan_build_range_impl(smb200_crs* m, SpmvPlan& p, int want_
         if (bytes * 3 < (uint64_t)ctx->l2_bytes * 2 && m->max_row_len <= 16) variant = SMB200_SPMV_SCALAR;
     }
     // RING needs short rows everywhere (its stages have no long-row path)
-    if (variant == SMB200_SPMV_RING && m->max_row_len > (uint64_t)kRowMajorMax) variant = SMB200_SPMV_STREAM;
+    if (variant == SMB200_SPMV_RING && m->max_row_len > (uint64_t)kRingRowMax) variant = SMB200_SPMV_STREAM;
     if (variant == SMB200_SPMV_BANDSPLIT) {
         // whole-matrix products only; a matrix of a single band (or a row range, or a distributed block) is STREAM's
         if (rb == 0 && re == m->n_rows && m->x_extra == 0 && rows > 0) {
@@ -1675,6 +1715,13 @@ static smb200_status plan_build_range_impl(smb200_crs* m, SpmvPlan& p, int want_
     p.variant = variant;
     p.lanes = 0;
     if (variant == SMB200_SPMV_SCALAR) p.lanes = 1;
+    if (variant == SMB200_SPMV_RING) {
+        // threads per row: 1 while a row fits 32 entries (storage-order sums), else the fewest that bring a lane's share to <= 32
+        p.lanes = 1;
+        while (p.lanes < 8 && m->max_row_len > (uint64_t)kRowMajorMax * (uint64_t)p.lanes) p.lanes *= 2;
+        const int forced = env_int("SMB200_RING_LANES", 0);
+        if (forced == 1 || forced == 2 || forced == 4 || forced == 8) p.lanes = forced;
+    }
     if (variant == SMB200_SPMV_VECTOR) {
         int l = want_lanes > 0 ? want_lanes : env_int("SMB200_SPMV_LANES", 0);
         if (l <= 0) l = pick_lanes(mean);
@@ -1800,8 +1847,11 @@ static smb200_status launch_typed(smb200_crs* m, const SpmvPlan& p, uint64_t rb,
             const size_t smem = stage * stages;
             SMB_REQUIRE(smem <= 224u * 1024u, SMB200_ERR_INVALID, "spmv: ring stage of %zu bytes does not fit shared memory", stage);
 
-            auto kern = spmv_ring_kernel<T, I, DOT, false>;
-            auto kern_d = spmv_ring_kernel<T, I, DOT, true>;
+            const int rl = p.lanes > 1 ? p.lanes : 1;        // threads per row (plan: from the longest row)
+            auto kern = rl == 8 ? spmv_ring_kernel<T, I, DOT, false, 8> : rl == 4 ? spmv_ring_kernel<T, I, DOT, false, 4>
+                      : rl == 2 ? spmv_ring_kernel<T, I, DOT, false, 2> : spmv_ring_kernel<T, I, DOT, false, 1>;
+            auto kern_d = rl == 8 ? spmv_ring_kernel<T, I, DOT, true, 8> : rl == 4 ? spmv_ring_kernel<T, I, DOT, true, 4>
+                        : rl == 2 ? spmv_ring_kernel<T, I, DOT, true, 2> : spmv_ring_kernel<T, I, DOT, true, 1>;
             if (g_halo.host) SMB_CUDA(cudaFuncSetAttribute(kern_d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             else SMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             int resident = 0;

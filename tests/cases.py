@@ -67,3 +67,35 @@ def abs_rowsum(values, columns, offsets, x):
 
 
 TOL = {np.dtype(np.float32): 1e-5, np.dtype(np.float64): 1e-12}   # BASELINE.json north_star
+
+
+def fem_like(nx, ny, nz, dof, vdt, idt, seed=0):
+    """27-point stencil with `dof` unknowns per grid node (a trilinear FEM vector problem): 27 * dof entries per interior
+    row, fewer at the boundary; columns ascending inside a row; values random (not symmetric: only the product is tested)."""
+    rng = np.random.default_rng(seed)
+    n_nodes = nx * ny * nz
+    node = np.arange(n_nodes)
+    ix, iy, iz = node % nx, (node // nx) % ny, node // (nx * ny)
+    parts = []
+    for dz in (-1, 0, 1):
+        for dy in (-1, 0, 1):
+            for dx in (-1, 0, 1):
+                ok = (ix + dx >= 0) & (ix + dx < nx) & (iy + dy >= 0) & (iy + dy < ny) & (iz + dz >= 0) & (iz + dz < nz)
+                parts.append(np.where(ok, node + dx + dy * nx + dz * nx * ny, -1))
+    nbs = np.stack(parts, 1)                                       # [n_nodes, 27], -1 = outside, ascending where valid
+    valid = nbs >= 0
+    per_node = valid.sum(1)
+    flat_nb = nbs[valid]                                           # per node, its valid neighbours in ascending order
+    # the columns of ONE row of each node: neighbour * dof + 0..dof-1
+    nb_exp = np.repeat(flat_nb, dof) * dof + np.tile(np.arange(dof), flat_nb.size)
+    exp_off = np.zeros(n_nodes + 1, np.int64)
+    np.cumsum(per_node * dof, out=exp_off[1:])
+    n_rows = n_nodes * dof
+    lens = np.repeat(per_node * dof, dof)                          # every unknown of a node has the node's column set
+    offs = np.zeros(n_rows + 1, np.int64)
+    np.cumsum(lens, out=offs[1:])
+    node_of_row = np.repeat(node, dof)
+    idx = np.arange(int(offs[-1])) - np.repeat(offs[:-1], lens) + np.repeat(exp_off[node_of_row], lens)
+    cols = nb_exp[idx]
+    vals = rng.uniform(-1.0, 1.0, cols.size).astype(vdt)
+    return n_rows, n_rows, vals, cols.astype(idt), offs.astype(idt)

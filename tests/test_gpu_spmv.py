@@ -37,7 +37,9 @@ def _check(smb, orc, ctx, case, seed=11, x_extra=0):
         assert y.dim() == n_rows                       # mvp returns a vector of dim n_rows (sparsematrix.rs:148-155)
         got = y.to_numpy()
         name = f"{info['variant_name']}/{lanes} {vals.dtype}/{cols.dtype} rows={n_rows} nnz={vals.size}"
-        exact = variant == smb.SPMV_SCALAR or (info["variant"] >= smb.SPMV_STREAM and max_len <= 64)
+        # storage-order row sums: one thread per row (stream kernels up to 64 entries, the ring with one lane per row)
+        exact = variant == smb.SPMV_SCALAR or (info["variant"] >= smb.SPMV_STREAM and max_len <= 64 and
+                                               not (info["variant"] == smb.SPMV_RING and info["lanes"] > 1))
         if exact:
             assert np.array_equal(got, want), f"{name}: not bit-exact ({np.count_nonzero(got != want)} rows differ)"
         else:
@@ -121,8 +123,8 @@ def test_host_buffer_pipeline_chunks(smb, orc, ctx, chunks, monkeypatch):
 @pytest.mark.parametrize("vdt,idt", COMBOS)
 def test_ring_kernel_windows_and_fallbacks(smb, orc, ctx, vdt, idt):
     """RING stages everything by TMA, including up to four windows of x per block.  Stencils get windows; a short-row matrix
-    with scattered columns gets none (global gathers); a borrowed, misaligned x must not be bulk-copied; long rows fall back
-    to STREAM.  All bit-exact (storage-order sums)."""
+    with scattered columns gets none (global gathers); a borrowed, misaligned x must not be bulk-copied; rows of 33..256 entries take
+    several lanes per row (tolerance), longer ones fall back to STREAM.  One lane per row: bit-exact (storage-order sums)."""
     for nx, ny, nz in [(40, 30, 1), (24, 20, 18)]:
         vals, cols, offs = orc.laplace(vdt, idt, nx, ny, nz)
         n = nx * ny * nz
@@ -152,8 +154,16 @@ def test_ring_kernel_windows_and_fallbacks(smb, orc, ctx, vdt, idt):
     assert a.plan_info()["stream_bytes"] == a.plan_info()["algorithmic_bytes"]
     x = np.random.default_rng(1).uniform(-1, 1, case[1]).astype(vdt)
     assert np.array_equal(a.mvp(smb.DenseVec.from_vec(ctx, x)).to_numpy(), orc.mvp(case[2], case[3], case[4], x))
-    long_rows = cases.ragged(42, 300, 5000, 90, vdt, idt)                      # rows > 32 entries: not RING's business
+    long_rows = cases.ragged(42, 300, 5000, 90, vdt, idt)                      # rows of 33..256 entries: several lanes per row
     a = smb.SparseMatCRS.from_raw_parts(ctx, *long_rows).configure(smb.SPMV_RING)
+    assert a.plan_info()["variant"] == smb.SPMV_RING and a.plan_info()["lanes"] == 4
+    x = np.random.default_rng(2).uniform(-1, 1, long_rows[1]).astype(vdt)
+    want = orc.mvp(long_rows[2], long_rows[3], long_rows[4], x)
+    got = a.mvp(smb.DenseVec.from_vec(ctx, x)).to_numpy()
+    scale = cases.abs_rowsum(long_rows[2], long_rows[3], long_rows[4], x) + np.finfo(np.float64).tiny
+    assert float((np.abs(got.astype(np.float64) - want.astype(np.float64)) / scale).max()) <= cases.TOL[np.dtype(vdt)]
+    longer = cases.ragged(43, 300, 5000, 400, vdt, idt)                        # rows > 256 entries: not RING's business
+    a = smb.SparseMatCRS.from_raw_parts(ctx, *longer).configure(smb.SPMV_RING)
     assert a.plan_info()["variant"] == smb.SPMV_STREAM
 
 
@@ -373,3 +383,34 @@ def test_bandsplit_column_bands(smb, orc, ctx, vdt, idt):
             assert np.allclose(xs.to_numpy(), xo, rtol=1e-8, atol=1e-10)
     finally:
         os.environ.pop("SMB200_BANDSPLIT_WIDTH", None)
+
+
+@pytest.mark.parametrize("vdt,idt", COMBOS)
+def test_ring_kernel_long_rows_multi_lane(smb, orc, ctx, vdt, idt):
+    """FEM-like rows of 33..256 entries (27-point stencil x dof unknowns per node) stay on the TMA ring: 2 / 4 / 8 threads per
+    row, strided partial sums + a fixed shuffle tree — deterministic, inside the north-star tolerance of the oracle's
+    storage-order sum (not bit-exact); rows of <= 32 entries keep one thread per row and stay bit-exact."""
+    tol = cases.TOL[np.dtype(vdt)]
+    for dof, lanes in ((1, 1), (2, 2), (3, 4), (6, 8)):
+        case = cases.fem_like(14, 11, 9, dof, vdt, idt, seed=dof)
+        n_rows, n_cols, vals, cols, offs = case
+        a = smb.SparseMatCRS.from_raw_parts(ctx, *case)
+        info = a.plan_info()
+        assert info["variant"] == smb.SPMV_RING and info["lanes"] == lanes, info            # AUTO keeps the ring
+        assert info["nnz_c16"] == vals.size                                                   # every block streams 16-bit columns
+        x = orc.uniform(vdt, 21, n_cols)
+        xd = smb.DenseVec.from_vec(ctx, x)
+        want = orc.mvp(vals, cols, offs, x)
+        got = a.mvp(xd).to_numpy()
+        if lanes == 1:
+            assert np.array_equal(got, want)
+        else:
+            scale = cases.abs_rowsum(vals, cols, offs, x) + np.finfo(np.float64).tiny
+            err = np.abs(got.astype(np.float64) - want.astype(np.float64)) / scale
+            assert float(err.max()) <= tol, (dof, float(err.max()))
+            assert np.array_equal(a.mvp(xd).to_numpy(), got)                                  # deterministic
+            # same numbers as the stream kernel within the tolerance, and the fused dot agrees
+            lhs = orc.uniform(vdt, 22, n_rows)
+            bil = float(a.inner_prod(smb.DenseVec.from_vec(ctx, lhs), xd))
+            ref = float(np.sum(lhs.astype(np.float64) * want.astype(np.float64)))
+            assert abs(bil - ref) <= 1e-5 * float(np.sum(np.abs(lhs.astype(np.float64)) * scale)) + 1e-30

@@ -56,6 +56,7 @@ def test_transpose_is_bit_exact(smb, orc, ctx, vdt, idt):
             tt = t.transpose()
             assert tt.n_non_zero_entries() == vals.size
             x = orc.uniform(vdt, 3, t.n_cols())
+            t.configure(smb.SPMV_SCALAR)                                  # one thread per row: the reference's storage-order sums
             assert np.array_equal(t.mvp(smb.DenseVec.from_vec(ctx, x)).to_numpy(), orc.mvp(wv, wcols, woffs, x))
 
 
