@@ -27,15 +27,40 @@ namespace smb {
 // distributed SpMV); contiguous so one all-reduce covers them.  Single GPU uses slot 0 only.
 // S_RR_LOCAL: multi-GPU only — the rank-local r.r, all-reduced OUT OF PLACE into S_RR_NEW (after the stop test
 // has fired the update kernels exit early and leave S_RR_LOCAL alone, so repeating the all-reduce is harmless).
-enum { S_RR = 0, S_PAP = 1, S_RR_NEW = 4, S_THRESH = 5, S_ITER = 6, S_DONE = 7, S_RR_LOCAL = 8, S_COUNT = 16 };
+// S_RES2: Jacobi-preconditioned solves only — r.r for the stop test (S_RR / S_RR_NEW then hold r.z, z = D^-1 r).
+enum { S_RR = 0, S_PAP = 1, S_RR_NEW = 4, S_THRESH = 5, S_ITER = 6, S_DONE = 7, S_RR_LOCAL = 8, S_RES2 = 9, S_COUNT = 16 };
 
 constexpr int kCgThreads = 256;
 
-// r = b - ap; p = r; S[RR_NEW] = r.r   (linearsolver.rs:38-40)
-template <class T>
+// Two grid-wide sums with one ticket (same pattern as reduce.cuh's grid_sum; partials holds 2 * nblocks doubles).
+template <int THREADS>
+__device__ __forceinline__ bool grid_sum2(double v0, double v1, double* __restrict__ partials, unsigned int* __restrict__ ticket,
+                                          double* scratch, double& t0, double& t1) {
+    __shared__ bool s_last2;
+    const unsigned int nblocks = gridDim.x;
+    if (threadIdx.x == 0) {
+        partials[blockIdx.x] = v0;
+        partials[nblocks + blockIdx.x] = v1;
+        __threadfence();
+        s_last2 = atomicAdd(ticket, 1u) == nblocks - 1;
+    }
+    __syncthreads();
+    if (!s_last2) return false;
+    __threadfence();
+    double a0 = 0.0, a1 = 0.0;
+    for (unsigned int i = threadIdx.x; i < nblocks; i += THREADS) { a0 += __ldcg(partials + i); a1 += __ldcg(partials + nblocks + i); }
+    t0 = block_sum<THREADS>(a0, scratch);
+    t1 = block_sum<THREADS>(a1, scratch);
+    if (threadIdx.x == 0) *ticket = 0u;
+    return true;
+}
+
+// r = b - ap; p = r; S[RR_NEW] = r.r   (linearsolver.rs:38-40).  PRE (Jacobi, additive): z = dinv * r; p = z; S[RR_NEW] = r.z
+template <class T, bool PRE>
 __global__ void __launch_bounds__(kCgThreads)
 cg_init_kernel(const T* __restrict__ b, const T* __restrict__ ap, T* __restrict__ r, T* __restrict__ p, uint64_t n,
-               double* __restrict__ S, int rr_slot, double* __restrict__ partials, unsigned int* __restrict__ ticket, int vec_ok) {
+               double* __restrict__ S, int rr_slot, double* __restrict__ partials, unsigned int* __restrict__ ticket, int vec_ok,
+               const T* __restrict__ dinv) {
     __shared__ double scratch[kCgThreads / 32 + 1];
     using V = typename Vec16<T>::type;
     constexpr int N = Vec16<T>::N;
@@ -46,24 +71,28 @@ cg_init_kernel(const T* __restrict__ b, const T* __restrict__ ap, T* __restrict_
 #pragma unroll
     for (int k = 0; k < N; ++k) lane_acc[k] = T(0);
     for (uint64_t i = tid; i < nvec; i += stride) {
-        Pack16<T> pb, pa;
+        Pack16<T> pb, pa, pz;
         pb.v = __ldg(reinterpret_cast<const V*>(b) + i);
         pa.v = __ldg(reinterpret_cast<const V*>(ap) + i);
+        if constexpr (PRE) pz.v = __ldg(reinterpret_cast<const V*>(dinv) + i);
 #pragma unroll
         for (int k = 0; k < N; ++k) {
             pb.e[k] = sub_rn(pb.e[k], pa.e[k]);
-            lane_acc[k] = add_rn(lane_acc[k], mul_rn(pb.e[k], pb.e[k]));
+            if constexpr (PRE) pz.e[k] = mul_rn(pz.e[k], pb.e[k]); else pz.e[k] = pb.e[k];
+            lane_acc[k] = add_rn(lane_acc[k], mul_rn(pb.e[k], pz.e[k]));
         }
         reinterpret_cast<V*>(r)[i] = pb.v;
-        reinterpret_cast<V*>(p)[i] = pb.v;
+        reinterpret_cast<V*>(p)[i] = pz.v;
     }
     double acc = 0.0;
 #pragma unroll
     for (int k = 0; k < N; ++k) acc += (double)lane_acc[k];
     for (uint64_t i = nvec * N + tid; i < n; i += stride) {
         const T v = sub_rn(b[i], ap[i]);
-        r[i] = v; p[i] = v;
-        acc += (double)mul_rn(v, v);
+        T z = v;
+        if constexpr (PRE) z = mul_rn(dinv[i], v);
+        r[i] = v; p[i] = z;
+        acc += (double)mul_rn(v, z);
     }
     const double bsum = block_sum<kCgThreads>(acc, scratch);
     double total;
@@ -72,10 +101,12 @@ cg_init_kernel(const T* __restrict__ b, const T* __restrict__ ap, T* __restrict_
 }
 
 // B: x += (p * alpha); r -= (ap * alpha); S[RR_NEW] = r.r      (linearsolver.rs:45-51)
-template <class T>
+//    PRE: S[RR_NEW] = r.(dinv * r) and S[RES2] = r.r
+template <class T, bool PRE>
 __global__ void __launch_bounds__(kCgThreads)
 cg_update_xr_kernel(T* __restrict__ x, T* __restrict__ r, const T* __restrict__ p, const T* __restrict__ ap, uint64_t n,
-                    double* __restrict__ S, int rr_slot, double* __restrict__ partials, unsigned int* __restrict__ ticket, int vec_ok) {
+                    double* __restrict__ S, int rr_slot, double* __restrict__ partials, unsigned int* __restrict__ ticket, int vec_ok,
+                    const T* __restrict__ dinv) {
     __shared__ double scratch[kCgThreads / 32 + 1];
     if (__ldcg(S + S_DONE) != 0.0) return;
     const T alpha = div_rn((T)__ldcg(S + S_RR), (T)(__ldcg(S + S_PAP) + __ldcg(S + S_PAP + 1) + __ldcg(S + S_PAP + 2)));
@@ -84,13 +115,14 @@ cg_update_xr_kernel(T* __restrict__ x, T* __restrict__ r, const T* __restrict__ 
     const uint64_t tid = blockIdx.x * (uint64_t)kCgThreads + threadIdx.x;
     const uint64_t stride = (uint64_t)gridDim.x * kCgThreads;
     const uint64_t nvec = vec_ok ? n / N : 0;      // a borrowed b / x (smb200_vec_wrap) may not be 16-byte aligned: element loop
-    T lane_acc[N];
+    T lane_acc[N], lane_acz[N];
 #pragma unroll
-    for (int k = 0; k < N; ++k) lane_acc[k] = T(0);
+    for (int k = 0; k < N; ++k) lane_acc[k] = lane_acz[k] = T(0);
     for (uint64_t i = tid; i < nvec; i += stride) {
-        Pack16<T> px, pr, pp, pa;
+        Pack16<T> px, pr, pp, pa, pd;
         pp.v = __ldg(reinterpret_cast<const V*>(p) + i);
         pa.v = __ldg(reinterpret_cast<const V*>(ap) + i);
+        if constexpr (PRE) pd.v = __ldg(reinterpret_cast<const V*>(dinv) + i);
         px.v = reinterpret_cast<V*>(x)[i];
         pr.v = reinterpret_cast<V*>(r)[i];
 #pragma unroll
@@ -98,33 +130,43 @@ cg_update_xr_kernel(T* __restrict__ x, T* __restrict__ r, const T* __restrict__ 
             px.e[k] = add_rn(px.e[k], mul_rn(pp.e[k], alpha));
             pr.e[k] = sub_rn(pr.e[k], mul_rn(pa.e[k], alpha));
             lane_acc[k] = add_rn(lane_acc[k], mul_rn(pr.e[k], pr.e[k]));
+            if constexpr (PRE) lane_acz[k] = add_rn(lane_acz[k], mul_rn(pr.e[k], mul_rn(pd.e[k], pr.e[k])));
         }
         reinterpret_cast<V*>(x)[i] = px.v;
         reinterpret_cast<V*>(r)[i] = pr.v;
     }
-    double acc = 0.0;
+    double acc = 0.0, acz = 0.0;
 #pragma unroll
-    for (int k = 0; k < N; ++k) acc += (double)lane_acc[k];
+    for (int k = 0; k < N; ++k) { acc += (double)lane_acc[k]; acz += (double)lane_acz[k]; }
     for (uint64_t i = nvec * N + tid; i < n; i += stride) {
         x[i] = add_rn(x[i], mul_rn(p[i], alpha));
         const T rv = sub_rn(r[i], mul_rn(ap[i], alpha));
         r[i] = rv;
         acc += (double)mul_rn(rv, rv);
+        if constexpr (PRE) acz += (double)mul_rn(rv, mul_rn(dinv[i], rv));
     }
-    const double bsum = block_sum<kCgThreads>(acc, scratch);
-    double total;
-    if (grid_sum<kCgThreads>(bsum, partials, ticket, scratch, total))
-        if (threadIdx.x == 0) S[rr_slot] = (double)(T)total;
+    if constexpr (PRE) {
+        const double b0 = block_sum<kCgThreads>(acc, scratch), b1 = block_sum<kCgThreads>(acz, scratch);
+        double t0, t1;
+        if (grid_sum2<kCgThreads>(b0, b1, partials, ticket, scratch, t0, t1))
+            if (threadIdx.x == 0) { S[S_RES2] = (double)(T)t0; S[rr_slot] = (double)(T)t1; }
+    } else {
+        const double bsum = block_sum<kCgThreads>(acc, scratch);
+        double total;
+        if (grid_sum<kCgThreads>(bsum, partials, ticket, scratch, total))
+            if (threadIdx.x == 0) S[rr_slot] = (double)(T)total;
+    }
 }
 
 // C: stop test, bookkeeping, p = (p * beta) + r                  (linearsolver.rs:52-59)
-template <class T>
+//    PRE: the stop test looks at r.r (S[RES2]), beta = r.z' / r.z, p = (p * beta) + dinv * r
+template <class T, bool PRE>
 __global__ void __launch_bounds__(kCgThreads)
 cg_update_p_kernel(T* __restrict__ p, const T* __restrict__ r, uint64_t n, double* __restrict__ S,
-                   double* __restrict__ history, uint64_t hist_cap) {
+                   double* __restrict__ history, uint64_t hist_cap, const T* __restrict__ dinv) {
     if (__ldcg(S + S_DONE) != 0.0) return;
     const double rr_new = __ldcg(S + S_RR_NEW);
-    const double res = sqrt(rr_new);                       // f64::sqrt(r_norm_squared.into())
+    const double res = sqrt(PRE ? __ldcg(S + S_RES2) : rr_new);     // f64::sqrt(r_norm_squared.into())
     const bool done = res < __ldcg(S + S_THRESH);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         const uint64_t it = (uint64_t)S[S_ITER];
@@ -140,14 +182,15 @@ cg_update_p_kernel(T* __restrict__ p, const T* __restrict__ r, uint64_t n, doubl
     const uint64_t stride = (uint64_t)gridDim.x * kCgThreads;
     const uint64_t nvec = n / N;
     for (uint64_t i = tid; i < nvec; i += stride) {
-        Pack16<T> pp, pr;
+        Pack16<T> pp, pr, pd;
         pp.v = reinterpret_cast<V*>(p)[i];
         pr.v = __ldg(reinterpret_cast<const V*>(r) + i);
+        if constexpr (PRE) pd.v = __ldg(reinterpret_cast<const V*>(dinv) + i);
 #pragma unroll
-        for (int k = 0; k < N; ++k) pp.e[k] = add_rn(mul_rn(pp.e[k], beta), pr.e[k]);
+        for (int k = 0; k < N; ++k) pp.e[k] = add_rn(mul_rn(pp.e[k], beta), PRE ? mul_rn(pd.e[k], pr.e[k]) : pr.e[k]);
         reinterpret_cast<V*>(p)[i] = pp.v;
     }
-    for (uint64_t i = nvec * N + tid; i < n; i += stride) p[i] = add_rn(mul_rn(p[i], beta), r[i]);
+    for (uint64_t i = nvec * N + tid; i < n; i += stride) p[i] = add_rn(mul_rn(p[i], beta), PRE ? mul_rn(dinv[i], r[i]) : r[i]);
 }
 
 void cg_free(CgWork& w) {
@@ -157,6 +200,7 @@ void cg_free(CgWork& w) {
     if (w.scalars) cudaFree(w.scalars);
     if (w.scalars_host) cudaFreeHost(w.scalars_host);
     if (w.history) cudaFree(w.history);
+    if (w.dinv) cudaFree(w.dinv);
     if (w.graph) cudaGraphExecDestroy(w.graph);
     w = CgWork();
 }
@@ -185,59 +229,64 @@ smb200_status cg_prepare(smb200_ctx* ctx, CgWork& w, int vt, uint64_t n, uint64_
         SMB_CUDA(cudaMalloc(&w.history, w.hist_cap * sizeof(double)));
         w.n = n;
     }
-    SMB_TRY(ensure_reduction_scratch(ctx, (size_t)ctx->sm_count * 8 + 16));
+    SMB_TRY(ensure_reduction_scratch(ctx, (size_t)ctx->sm_count * 16 + 16));     // two partials per CTA (preconditioned x/r update)
     return SMB200_OK;
 }
 
-smb200_status cg_init_launch(smb200_ctx* ctx, CgWork& w, int vt, const void* b, uint64_t n) {
+smb200_status cg_init_launch(smb200_ctx* ctx, CgWork& w, int vt, const void* b, uint64_t n, const void* dinv) {
     const unsigned g = cg_grid(ctx, n, vt);
     const int slot = ctx->world > 1 ? S_RR_LOCAL : S_RR_NEW;
     const int vec_ok = ((uintptr_t)b & 15u) == 0 ? 1 : 0;
-    if (vt == SMB200_F64) cg_init_kernel<double><<<g, kCgThreads, 0, ctx->stream>>>((const double*)b, (const double*)w.ap, (double*)w.r, (double*)w.p, n, w.scalars, slot, ctx->red_partials, ctx->red_ticket, vec_ok);
-    else cg_init_kernel<float><<<g, kCgThreads, 0, ctx->stream>>>((const float*)b, (const float*)w.ap, (float*)w.r, (float*)w.p, n, w.scalars, slot, ctx->red_partials, ctx->red_ticket, vec_ok);
+    if (dinv) {
+        if (vt == SMB200_F64) cg_init_kernel<double, true><<<g, kCgThreads, 0, ctx->stream>>>((const double*)b, (const double*)w.ap, (double*)w.r, (double*)w.p, n, w.scalars, slot, ctx->red_partials, ctx->red_ticket, vec_ok, (const double*)dinv);
+        else cg_init_kernel<float, true><<<g, kCgThreads, 0, ctx->stream>>>((const float*)b, (const float*)w.ap, (float*)w.r, (float*)w.p, n, w.scalars, slot, ctx->red_partials, ctx->red_ticket, vec_ok, (const float*)dinv);
+    } else if (vt == SMB200_F64) cg_init_kernel<double, false><<<g, kCgThreads, 0, ctx->stream>>>((const double*)b, (const double*)w.ap, (double*)w.r, (double*)w.p, n, w.scalars, slot, ctx->red_partials, ctx->red_ticket, vec_ok, nullptr);
+    else cg_init_kernel<float, false><<<g, kCgThreads, 0, ctx->stream>>>((const float*)b, (const float*)w.ap, (float*)w.r, (float*)w.p, n, w.scalars, slot, ctx->red_partials, ctx->red_ticket, vec_ok, nullptr);
     count_launch();
     SMB_CUDA(cudaGetLastError());
     return SMB200_OK;
 }
 
-smb200_status cg_xr_launch(smb200_ctx* ctx, CgWork& w, int vt, void* x, uint64_t n) {
+smb200_status cg_xr_launch(smb200_ctx* ctx, CgWork& w, int vt, void* x, uint64_t n, const void* dinv) {
     const unsigned g = cg_grid(ctx, n, vt);
     const int slot = ctx->world > 1 ? S_RR_LOCAL : S_RR_NEW;
     const int vec_ok = ((uintptr_t)x & 15u) == 0 ? 1 : 0;
-    if (vt == SMB200_F64) cg_update_xr_kernel<double><<<g, kCgThreads, 0, ctx->stream>>>((double*)x, (double*)w.r, (const double*)w.p, (const double*)w.ap, n, w.scalars, slot, ctx->red_partials, ctx->red_ticket, vec_ok);
-    else cg_update_xr_kernel<float><<<g, kCgThreads, 0, ctx->stream>>>((float*)x, (float*)w.r, (const float*)w.p, (const float*)w.ap, n, w.scalars, slot, ctx->red_partials, ctx->red_ticket, vec_ok);
+    if (dinv) {
+        if (vt == SMB200_F64) cg_update_xr_kernel<double, true><<<g, kCgThreads, 0, ctx->stream>>>((double*)x, (double*)w.r, (const double*)w.p, (const double*)w.ap, n, w.scalars, slot, ctx->red_partials, ctx->red_ticket, vec_ok, (const double*)dinv);
+        else cg_update_xr_kernel<float, true><<<g, kCgThreads, 0, ctx->stream>>>((float*)x, (float*)w.r, (const float*)w.p, (const float*)w.ap, n, w.scalars, slot, ctx->red_partials, ctx->red_ticket, vec_ok, (const float*)dinv);
+    } else if (vt == SMB200_F64) cg_update_xr_kernel<double, false><<<g, kCgThreads, 0, ctx->stream>>>((double*)x, (double*)w.r, (const double*)w.p, (const double*)w.ap, n, w.scalars, slot, ctx->red_partials, ctx->red_ticket, vec_ok, nullptr);
+    else cg_update_xr_kernel<float, false><<<g, kCgThreads, 0, ctx->stream>>>((float*)x, (float*)w.r, (const float*)w.p, (const float*)w.ap, n, w.scalars, slot, ctx->red_partials, ctx->red_ticket, vec_ok, nullptr);
     count_launch();
     SMB_CUDA(cudaGetLastError());
     return SMB200_OK;
 }
 
-smb200_status cg_p_launch(smb200_ctx* ctx, CgWork& w, int vt, uint64_t n) {
+smb200_status cg_p_launch(smb200_ctx* ctx, CgWork& w, int vt, uint64_t n, const void* dinv) {
     const unsigned g = cg_grid(ctx, n, vt);
-    if (vt == SMB200_F64) cg_update_p_kernel<double><<<g, kCgThreads, 0, ctx->stream>>>((double*)w.p, (const double*)w.r, n, w.scalars, w.history, w.hist_cap);
-    else cg_update_p_kernel<float><<<g, kCgThreads, 0, ctx->stream>>>((float*)w.p, (const float*)w.r, n, w.scalars, w.history, w.hist_cap);
+    if (dinv) {
+        if (vt == SMB200_F64) cg_update_p_kernel<double, true><<<g, kCgThreads, 0, ctx->stream>>>((double*)w.p, (const double*)w.r, n, w.scalars, w.history, w.hist_cap, (const double*)dinv);
+        else cg_update_p_kernel<float, true><<<g, kCgThreads, 0, ctx->stream>>>((float*)w.p, (const float*)w.r, n, w.scalars, w.history, w.hist_cap, (const float*)dinv);
+    } else if (vt == SMB200_F64) cg_update_p_kernel<double, false><<<g, kCgThreads, 0, ctx->stream>>>((double*)w.p, (const double*)w.r, n, w.scalars, w.history, w.hist_cap, nullptr);
+    else cg_update_p_kernel<float, false><<<g, kCgThreads, 0, ctx->stream>>>((float*)w.p, (const float*)w.r, n, w.scalars, w.history, w.hist_cap, nullptr);
     count_launch();
     SMB_CUDA(cudaGetLastError());
     return SMB200_OK;
 }
 
 // One CG iteration on the context stream (single GPU).
-static smb200_status cg_iteration(smb200_crs* a, void* x) {
+static smb200_status cg_iteration(smb200_crs* a, void* x, const void* dinv) {
     smb200_ctx* ctx = a->ctx;
     CgWork& w = a->cg;
     SMB_TRY(spmv_launch_cg(a, a->plan, 0, a->n_rows, w.p, w.ap, w.p, w.scalars, 0, true));
-    SMB_TRY(cg_xr_launch(ctx, w, a->vt, x, a->n_rows));
-    SMB_TRY(cg_p_launch(ctx, w, a->vt, a->n_rows));
+    SMB_TRY(cg_xr_launch(ctx, w, a->vt, x, a->n_rows, dinv));
+    SMB_TRY(cg_p_launch(ctx, w, a->vt, a->n_rows, dinv));
     return SMB200_OK;
 }
 
-}  // namespace smb
-
-using namespace smb;
-
-extern "C" {
-
-smb200_status smb200_cg_solve(smb200_crs* a, const smb200_vec* b, smb200_vec* x, double tol, int32_t relative,
-                              uint64_t iter_max, smb200_cg_stats* stats) {
+// The solver behind smb200_cg_solve (dinv == nullptr: the reference's ConjugateGradient) and smb200_pcg_jacobi_solve
+// (dinv = 1 / diag(A): the additive Jacobi-preconditioned variant, same kernels with one more operand).
+smb200_status cg_solve_impl(smb200_crs* a, const smb200_vec* b, smb200_vec* x, double tol, int32_t relative,
+                            uint64_t iter_max, smb200_cg_stats* stats, const void* dinv) {
     SMB_REQUIRE(a && b && x, SMB200_ERR_INVALID, "cg_solve: NULL argument");
     SMB_REQUIRE(b->vt == a->vt && x->vt == a->vt, SMB200_ERR_INVALID, "cg_solve: value types differ");
     SMB_REQUIRE(b->ctx == a->ctx && x->ctx == a->ctx, SMB200_ERR_INVALID, "cg_solve: operands belong to different contexts");
@@ -274,7 +323,7 @@ smb200_status smb200_cg_solve(smb200_crs* a, const smb200_vec* b, smb200_vec* x,
     const smb200_status st0 = spmv_launch_plan(a, a->plan, 0, n, x->d, w.ap, nullptr, 0);
     g_x_unpadded = false;
     SMB_TRY(st0);
-    SMB_TRY(cg_init_launch(ctx, w, a->vt, b->d, n));
+    SMB_TRY(cg_init_launch(ctx, w, a->vt, b->d, n, dinv));
 
     const char* genv = getenv("SMB200_CG_GRAPH");
     const bool use_graph = !(genv && genv[0] == '0');
@@ -290,7 +339,7 @@ smb200_status smb200_cg_solve(smb200_crs* a, const smb200_vec* b, smb200_vec* x,
     uint64_t rounds = 0;
     bool finished = false;
     // first iteration eagerly: performs every lazy initialisation outside of stream capture
-    if (iter_max > 0) { st = cg_iteration(a, x->d); launched = 1; }
+    if (iter_max > 0) { st = cg_iteration(a, x->d, dinv); launched = 1; }
     while (st == SMB200_OK && !finished) {
         // publish (iteration, done) of everything launched so far
         const int slot = (int)(rounds & 1);
@@ -302,12 +351,12 @@ smb200_status smb200_cg_solve(smb200_crs* a, const smb200_vec* b, smb200_vec* x,
         if (nb > 0) {
             if (use_graph && nb == (uint64_t)batch) {
                 if (!w.graph || w.graph_batch != batch || w.graph_x != x->d || w.graph_partials != ctx->red_partials ||
-                    w.graph_plan != a->plan.blk_rows) {
+                    w.graph_plan != a->plan.blk_rows || w.graph_dinv != dinv) {
                     if (w.graph) { cudaGraphExecDestroy(w.graph); w.graph = nullptr; }
                     cudaGraph_t graph = nullptr;
                     e = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal);
                     if (e == cudaSuccess) {
-                        for (int k = 0; k < batch && st == SMB200_OK; ++k) st = cg_iteration(a, x->d);
+                        for (int k = 0; k < batch && st == SMB200_OK; ++k) st = cg_iteration(a, x->d, dinv);
                         cudaError_t e2 = cudaStreamEndCapture(ctx->stream, &graph);
                         if (st == SMB200_OK && e2 != cudaSuccess) e = e2;
                     }
@@ -319,12 +368,13 @@ smb200_status smb200_cg_solve(smb200_crs* a, const smb200_vec* b, smb200_vec* x,
                     w.graph_x = x->d;
                     w.graph_partials = ctx->red_partials;
                     w.graph_plan = a->plan.blk_rows;
+                    w.graph_dinv = dinv;
                 }
                 e = cudaGraphLaunch(w.graph, ctx->stream);
                 if (e != cudaSuccess) { set_error("cg_solve: graph launch failed: %s", cudaGetErrorString(e)); st = SMB200_ERR_CUDA; break; }
                 count_launch(4 * (uint64_t)batch);   // SpMV+dot, dot finalize, x/r update, p update
             } else {
-                for (uint64_t k = 0; k < nb && st == SMB200_OK; ++k) st = cg_iteration(a, x->d);
+                for (uint64_t k = 0; k < nb && st == SMB200_OK; ++k) st = cg_iteration(a, x->d, dinv);
                 if (st != SMB200_OK) break;
             }
             launched += nb;
@@ -351,7 +401,7 @@ smb200_status smb200_cg_solve(smb200_crs* a, const smb200_vec* b, smb200_vec* x,
             cudaMemcpy(w.history_host.data(), w.history, w.history_host.size() * sizeof(double), cudaMemcpyDeviceToHost);
         if (stats) {
             stats->iterations = iters;
-            stats->final_residual = sqrt(S[S_RR_NEW]);
+            stats->final_residual = sqrt(dinv ? S[S_RES2] : S[S_RR_NEW]);
             stats->converged = S[S_DONE] != 0.0;
             cudaEventElapsedTime(&stats->device_ms, ev0, ev1);
             stats->launches = g_launches - launches0;
@@ -362,6 +412,17 @@ smb200_status smb200_cg_solve(smb200_crs* a, const smb200_vec* b, smb200_vec* x,
     cudaEventDestroy(ev0); cudaEventDestroy(ev1);
     cudaEventDestroy(poll_ev[0]); cudaEventDestroy(poll_ev[1]);
     return st;
+}
+
+}  // namespace smb
+
+using namespace smb;
+
+extern "C" {
+
+smb200_status smb200_cg_solve(smb200_crs* a, const smb200_vec* b, smb200_vec* x, double tol, int32_t relative,
+                              uint64_t iter_max, smb200_cg_stats* stats) {
+    return cg_solve_impl(a, b, x, tol, relative, iter_max, stats, nullptr);
 }
 
 smb200_status smb200_cg_history(const smb200_crs* a, double* out, uint64_t cap, uint64_t* n) {

@@ -165,6 +165,9 @@ struct CgWork {
     const void* graph_x = nullptr;      // pointers the graph was captured with
     const void* graph_partials = nullptr;
     const void* graph_plan = nullptr;
+    const void* graph_dinv = nullptr;   // Jacobi-preconditioned batch: the inverse diagonal it was captured with
+    void* dinv = nullptr;               // 1 / diag(A) of the last preconditioned solve (n elements)
+    uint64_t dinv_n = 0;
 };
 
 }  // namespace smb
@@ -237,9 +240,11 @@ smb200_status gen_laplace_block(smb200_ctx* ctx, int vt, int it, uint64_t nx, ui
                                 uint64_t row_hi, int local_cols, uint64_t n_lo_ghost, uint64_t n_cols_out,
                                 smb200_crs** out, uint64_t ghost_base = 0);   // ghost_base 0: ghosts right behind the owned columns
 smb200_status cg_prepare(smb200_ctx* ctx, CgWork& w, int vt, uint64_t n, uint64_t p_cap, uint64_t iter_max);
-smb200_status cg_init_launch(smb200_ctx* ctx, CgWork& w, int vt, const void* b, uint64_t n);
-smb200_status cg_xr_launch(smb200_ctx* ctx, CgWork& w, int vt, void* x, uint64_t n);
-smb200_status cg_p_launch(smb200_ctx* ctx, CgWork& w, int vt, uint64_t n);
+smb200_status cg_init_launch(smb200_ctx* ctx, CgWork& w, int vt, const void* b, uint64_t n, const void* dinv = nullptr);
+smb200_status cg_xr_launch(smb200_ctx* ctx, CgWork& w, int vt, void* x, uint64_t n, const void* dinv = nullptr);
+smb200_status cg_p_launch(smb200_ctx* ctx, CgWork& w, int vt, uint64_t n, const void* dinv = nullptr);
+smb200_status cg_solve_impl(smb200_crs* a, const smb200_vec* b, smb200_vec* x, double tol, int32_t relative,
+                            uint64_t iter_max, smb200_cg_stats* stats, const void* dinv);
 
 // y = A x on m->ctx->stream.  If dot_out != nullptr, also accumulates sum_r w[r]*y[r] into the
 // reduction scratch and leaves the result in ctx->red_result[slot] (fused SpMV + dot, K7a).

@@ -1,16 +1,17 @@
 // Jacobi-preconditioned CG — additive, NOT in the reference (the LinearSolver trait of
-// linearsolver.rs:6-10 has one implementation, the unpreconditioned ConjugateGradient).  First version: composed from
-// the validated primitives (smb200_spmv, vec_dot, vec_axpy, vec_scale_add) plus two small kernels (diagonal, elementwise
-// product); the scalars alpha / beta live on the host, so every iteration synchronises three times.  The arithmetic
-// follows the reference's conventions: everything in T, products rounded before they are added (never an FMA), the stop
-// test sqrt(r.r) < tol (absolute; `relative` scales tol by ||b||) evaluated in f64 after the x / r update.
+// linearsolver.rs:6-10 has one implementation, the unpreconditioned ConjugateGradient).  The solver is cg.cu's: the same
+// three fused kernels per iteration with the inverse diagonal as one more operand (z = D^-1 r is never stored), alpha, beta,
+// r.z, r.r and the stop test on the device, iterations replayed from a CUDA graph — no host synchronisation in the loop.
+// This file holds the diagonal extraction and the entry point.  The arithmetic follows the reference's conventions:
+// everything in T, products rounded before they are added (never an FMA), the stop test sqrt(r.r) < tol (absolute;
+// `relative` scales tol by ||b||) evaluated in f64 after the x / r update.
 //
 //   r = b - A x;  z = D^-1 r;  p = z;  rz = r.z
 //   loop:  Ap = A p;  alpha = rz / p.Ap;  x += p alpha;  r -= Ap alpha;  stop if sqrt(r.r) < tol
 //          z = D^-1 r;  beta = r.z / rz;  p = p beta + z
 //
-// Checked on hardware against the same recurrence in numpy (tests/test_gpu_pcg.py); not yet tuned: a device-scalar,
-// graph-replayed version like cg.cu's is the obvious next step.
+// Algorithmic bytes per iteration: SpMV + 11 N sizeof(T).  Checked on hardware against the same recurrence in numpy
+// (tests/test_gpu_pcg.py; there is no reference implementation to compare with).
 #include "common.cuh"
 #include "reduce.cuh"
 
@@ -40,28 +41,6 @@ __global__ void reciprocal_kernel(const T* d, uint64_t n, T* inv, unsigned long 
     if (v == T(0)) { atomicAdd(zeros, 1ull); inv[i] = T(0); }
     else inv[i] = T(1) / v;
 }
-
-// z[i] = w[i] * r[i]
-template <class T>
-__global__ void multiply_kernel(const T* __restrict__ w, const T* __restrict__ r, uint64_t n, T* __restrict__ z) {
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += stride) z[i] = mul_rn(w[i], r[i]);
-}
-
-template <class T>
-static smb200_status multiply_launch(smb200_ctx* ctx, const void* w, const void* r, uint64_t n, void* z) {
-    if (n == 0) return SMB200_OK;
-    uint64_t g = (n + 255) / 256, cap = (uint64_t)ctx->sm_count * 8;
-    multiply_kernel<T><<<(unsigned)(g < cap ? g : cap), 256, 0, ctx->stream>>>((const T*)w, (const T*)r, n, (T*)z);
-    count_launch();
-    SMB_CUDA(cudaGetLastError());
-    return SMB200_OK;
-}
-
-struct VecGuard {          // frees the solver's temporaries on every exit path
-    smb200_vec* v[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    ~VecGuard() { for (smb200_vec* p : v) if (p) smb200_vec_free(p); }
-};
 
 }  // namespace smb
 
@@ -98,30 +77,27 @@ smb200_status smb200_pcg_jacobi_solve(smb200_crs* a, const smb200_vec* b, smb200
     SMB_REQUIRE(a->n_rows == b->n && a->n_rows == x->n, SMB200_ERR_SIZE_MISMATCH, "Matrix and vector size mismatch");
     smb200_ctx* ctx = a->ctx;
     const uint64_t n = a->n_rows;
-    const smb200_vtype vt = (smb200_vtype)a->vt;
-    const uint64_t launches0 = g_launches;
-    smb200_cg_stats st_out;
-    memset(&st_out, 0, sizeof st_out);
-    if (n == 0) { if (stats) *stats = st_out; return SMB200_OK; }
-
-    VecGuard tmp;
-    for (int k = 0; k < 5; ++k) SMB_TRY(smb200_vec_create(ctx, vt, n, &tmp.v[k]));
-    smb200_vec *r = tmp.v[0], *z = tmp.v[1], *p = tmp.v[2], *ap = tmp.v[3], *dinv = tmp.v[4];
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    SMB_CUDA(cudaEventCreate(&ev0));
-    if (cudaEventCreate(&ev1) != cudaSuccess) { cudaEventDestroy(ev0); SMB_FAIL(SMB200_ERR_CUDA, "pcg_jacobi_solve: cudaEventCreate failed"); }
-    struct EvGuard { cudaEvent_t a, b; ~EvGuard() { cudaEventDestroy(a); cudaEventDestroy(b); } } evg{ev0, ev1};
-    SMB_CUDA(cudaEventRecord(ev0, ctx->stream));
-
-    // D^-1
-    SMB_TRY(smb200_crs_diagonal(a, dinv));
+    if (n == 0) { if (stats) memset(stats, 0, sizeof *stats); return SMB200_OK; }
+    SMB_CUDA(cudaSetDevice(ctx->device));
+    // D^-1, kept with the matrix's solver workspace (recomputed per solve: the values may have been scaled since)
+    CgWork& w = a->cg;
+    SMB_TRY(cg_prepare(ctx, w, a->vt, n, n, iter_max));       // first: (re)allocating the workspace releases an older dinv
+    if (!w.dinv || w.dinv_n != n) {
+        cudaStreamSynchronize(ctx->stream);
+        if (w.dinv) { cudaFree(w.dinv); w.dinv = nullptr; }
+        SMB_TRY(dev_alloc(&w.dinv, n * vsize(a->vt)));
+        w.dinv_n = n;
+    }
+    smb200_vec dv;
+    dv.ctx = ctx; dv.vt = a->vt; dv.n = n; dv.cap = n; dv.d = w.dinv; dv.owned = false;
+    SMB_TRY(smb200_crs_diagonal(a, &dv));
     unsigned long long* d_zeros = nullptr;
     SMB_CUDA(cudaMalloc(&d_zeros, sizeof(unsigned long long)));
     cudaMemsetAsync(d_zeros, 0, sizeof(unsigned long long), ctx->stream);
     {
         const unsigned g = (unsigned)((n + 255) / 256);
-        if (vt == SMB200_F64) reciprocal_kernel<double><<<g, 256, 0, ctx->stream>>>((const double*)dinv->d, n, (double*)dinv->d, d_zeros);
-        else reciprocal_kernel<float><<<g, 256, 0, ctx->stream>>>((const float*)dinv->d, n, (float*)dinv->d, d_zeros);
+        if (a->vt == SMB200_F64) reciprocal_kernel<double><<<g, 256, 0, ctx->stream>>>((const double*)w.dinv, n, (double*)w.dinv, d_zeros);
+        else reciprocal_kernel<float><<<g, 256, 0, ctx->stream>>>((const float*)w.dinv, n, (float*)w.dinv, d_zeros);
         count_launch();
     }
     unsigned long long h_zeros = 0;
@@ -130,56 +106,9 @@ smb200_status smb200_pcg_jacobi_solve(smb200_crs* a, const smb200_vec* b, smb200
     cudaFree(d_zeros);
     SMB_CUDA(e);
     SMB_REQUIRE(h_zeros == 0, SMB200_ERR_INVALID, "pcg_jacobi_solve: %llu rows have no (or a zero) diagonal entry", h_zeros);
-
-    auto mul = [&](const smb200_vec* w, const smb200_vec* rr, smb200_vec* out) {
-        return vt == SMB200_F64 ? multiply_launch<double>(ctx, w->d, rr->d, n, out->d) : multiply_launch<float>(ctx, w->d, rr->d, n, out->d);
-    };
-    // scalars are rounded to T like the reference's (alpha, beta and the dot products are `T`)
-    auto to_t = [&](double v) { return vt == SMB200_F64 ? v : (double)(float)v; };
-
-    double bb = 0.0, threshold = tol;
-    if (relative) { SMB_TRY(smb200_vec_dot(b, b, &bb)); threshold = tol * std::sqrt(bb); }
-    // r = b - A x   (b.clone() - mat.mvp(x), linearsolver.rs:38)
-    SMB_TRY(smb200_spmv(a, x, ap));
-    SMB_TRY(smb200_vec_copy(r, b));
-    SMB_TRY(smb200_vec_sub(r, ap));
-    SMB_TRY(mul(dinv, r, z));
-    SMB_TRY(smb200_vec_copy(p, z));
-    double rz = 0.0, rr = 0.0;
-    SMB_TRY(smb200_vec_dot(r, z, &rz));
-    SMB_TRY(smb200_vec_dot(r, r, &rr));
-    double res = std::sqrt(rr);
-    uint64_t it = 0;
-    int converged = 0;
-    for (uint64_t k = 0; k < iter_max; ++k) {
-        SMB_TRY(smb200_spmv(a, p, ap));
-        double pap = 0.0;
-        SMB_TRY(smb200_vec_dot(p, ap, &pap));
-        const double alpha = to_t(rz / pap);
-        SMB_TRY(smb200_vec_axpy(x, alpha, p));                 // *x += p.clone() * alpha
-        SMB_TRY(smb200_vec_axpy(r, -alpha, ap));               // r -= Ap * alpha  (the product's sign flip is exact)
-        SMB_TRY(smb200_vec_dot(r, r, &rr));
-        it = k + 1;
-        res = std::sqrt(rr);
-        if (res < threshold) { converged = 1; break; }
-        SMB_TRY(mul(dinv, r, z));
-        double rz_new = 0.0;
-        SMB_TRY(smb200_vec_dot(r, z, &rz_new));
-        const double beta = to_t(rz_new / rz);
-        SMB_TRY(smb200_vec_scale_add(p, beta, z));             // p = p * beta + z
-        rz = rz_new;
-    }
-    SMB_CUDA(cudaEventRecord(ev1, ctx->stream));
-    SMB_CUDA(cudaEventSynchronize(ev1));
-    float ms = 0.f;
-    SMB_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
-    st_out.iterations = it;
-    st_out.final_residual = res;
-    st_out.converged = converged;
-    st_out.device_ms = ms;
-    st_out.launches = g_launches - launches0;
-    if (stats) *stats = st_out;
-    return SMB200_OK;
+    // the CG machinery of cg.cu with one more operand: scalars on the device, iterations replayed from a CUDA graph, no
+    // host synchronisation inside the loop
+    return cg_solve_impl(a, b, x, tol, relative, iter_max, stats, w.dinv);
 }
 
 }  // extern "C"
