@@ -274,6 +274,28 @@ smb200_status smb200_pcg_jacobi_solve(smb200_crs* a, const smb200_vec* b, smb200
 /* R = max_n_rows / n_blocks; row -> (min(row / R, n_blocks), row - block*R).  ERR_INVALID on R == 0. */
 smb200_status smb200_par_locate(uint64_t n_blocks, uint64_t max_n_rows, uint64_t row, uint64_t* block,
                                 uint64_t* local_row);
+/* SparseMatPar (sparsemat_par.rs:12-35) with device-resident blocks and the `mvp_par` the reference left unfinished
+ * (sparsemat_par.rs:37-68).  Block b = global rows [b R, (b+1) R), R = max_n_rows / n_blocks, local row ids, GLOBAL column
+ * ids.  With a communicator (smb200_comm_init) block b lives on rank b * world / n_blocks and every rank makes the same
+ * calls; set_block_* read their arrays only on the block's owner.  ERR_INVALID for n_blocks == 0 or R == 0 (the reference
+ * divides by zero there).  par_mvp: x is the whole right-hand side on every rank (the sketch's `Arc<rhs>`), y is complete
+ * on every rank afterwards (the channel gather); a short block in front of later rows is ERR_INVALID "index out of
+ * bounds" (the reference's default mvp panics in IndexList::iter_row, indexlist.rs:88).  out3 of par_dims = {n_rows
+ * (scan up to the first empty block, sparsemat_par.rs:95-107), n_cols, non-zeros}.  par_block lends the device block
+ * (NULL when it is empty or lives on another rank). */
+typedef struct smb200_par smb200_par;
+smb200_status smb200_par_create(smb200_ctx* ctx, uint64_t n_blocks, uint64_t max_n_rows, smb200_vtype vt, smb200_itype it,
+                                smb200_par** out);
+smb200_status smb200_par_free(smb200_par* p);
+smb200_status smb200_par_owner(const smb200_par* p, uint64_t block, int32_t* rank);
+smb200_status smb200_par_set_block_indexlist(smb200_par* p, uint64_t block, uint64_t n_rows, uint64_t n_cols, uint64_t nnz,
+                                             const void* columns, const void* values, const void* pos_start,
+                                             const void* index_list);
+smb200_status smb200_par_set_block_crs(smb200_par* p, uint64_t block, uint64_t n_rows, uint64_t n_cols, uint64_t nnz,
+                                       const void* values, const void* columns, const void* offset_rows);
+smb200_status smb200_par_dims(const smb200_par* p, uint64_t* out3);
+smb200_status smb200_par_block(smb200_par* p, uint64_t block, smb200_crs** out);
+smb200_status smb200_par_mvp(smb200_par* p, const smb200_vec* x, smb200_vec* y);
 /* Contiguous row ranges for `world` ranks: rows_per_rank = ceil(n_rows / world) rounded up to a
  * multiple of `align` (e.g. one z-plane); out_bounds has world+1 entries. */
 smb200_status smb200_partition_rows(uint64_t n_rows, uint32_t world, uint64_t align, uint64_t* out_bounds);

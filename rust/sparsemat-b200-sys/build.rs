@@ -12,7 +12,7 @@ fn main() {
     // the same translation units as sparsemat_b200/csrc/Makefile (SRCS_CU, SRCS_CPP, SRCS_HOST); tests/test_abi_and_host.py
     // fails when the two lists drift apart
     let sources = ["context.cu", "vector_ops.cu", "crs.cu", "generators.cu", "spmv.cu", "bandsplit.cu", "cg.cu", "pcg.cu", "dist.cu",
-                   "transpose.cu", "partition.cpp", "crs_io.cpp", "../host/assembler_capi.cpp"];
+                   "transpose.cu", "par.cu", "partition.cpp", "crs_io.cpp", "../host/assembler_capi.cpp"];
     let mut objects = Vec::new();
     for s in sources.iter() {
         let obj = out.join(format!("{}.o", s.replace("../", "").replace("/", "_")));

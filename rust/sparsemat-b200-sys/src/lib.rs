@@ -24,6 +24,7 @@ pub const SMB200_U64: i32 = 1;
 #[repr(C)] pub struct smb200_crs { _p: [u8; 0] }
 #[repr(C)] pub struct smb200_event { _p: [u8; 0] }
 #[repr(C)] pub struct smb200_dist { _p: [u8; 0] }
+#[repr(C)] pub struct smb200_par { _p: [u8; 0] }
 
 #[repr(C)]
 #[derive(Clone, Copy)]
@@ -144,6 +145,16 @@ extern "C" {
                                    iter_max: u64, stats: *mut smb200_cg_stats) -> smb200_status;
 
     pub fn smb200_par_locate(n_blocks: u64, max_n_rows: u64, row: u64, block: *mut u64, local_row: *mut u64) -> smb200_status;
+    pub fn smb200_par_create(ctx: *mut smb200_ctx, n_blocks: u64, max_n_rows: u64, vt: i32, it: i32, out: *mut *mut smb200_par) -> smb200_status;
+    pub fn smb200_par_free(p: *mut smb200_par) -> smb200_status;
+    pub fn smb200_par_owner(p: *const smb200_par, block: u64, rank: *mut i32) -> smb200_status;
+    pub fn smb200_par_set_block_indexlist(p: *mut smb200_par, block: u64, n_rows: u64, n_cols: u64, nnz: u64, columns: *const c_void,
+                                          values: *const c_void, pos_start: *const c_void, index_list: *const c_void) -> smb200_status;
+    pub fn smb200_par_set_block_crs(p: *mut smb200_par, block: u64, n_rows: u64, n_cols: u64, nnz: u64, values: *const c_void,
+                                    columns: *const c_void, offset_rows: *const c_void) -> smb200_status;
+    pub fn smb200_par_dims(p: *const smb200_par, out3: *mut u64) -> smb200_status;
+    pub fn smb200_par_block(p: *mut smb200_par, block: u64, out: *mut *mut smb200_crs) -> smb200_status;
+    pub fn smb200_par_mvp(p: *mut smb200_par, x: *const smb200_vec, y: *mut smb200_vec) -> smb200_status;
     pub fn smb200_partition_rows(n_rows: u64, world: u32, align: u64, out_bounds: *mut u64) -> smb200_status;
     pub fn smb200_partition_rows_by_nnz(it: i32, n_rows: u64, offset_rows: *const c_void, world: u32, out_bounds: *mut u64) -> smb200_status;
     pub fn smb200_ghost_plan(it: i32, nnz: u64, columns_global: *const c_void, world: u32, rank: u32, bounds: *const u64,

@@ -128,6 +128,14 @@ PROTOTYPES = {
     "smb200_crs_diagonal": (_i32, [_p, _p]),
     "smb200_pcg_jacobi_solve": (_i32, [_p, _p, _p, C.c_double, _i32, _u64, C.POINTER(CgStats)]),
     "smb200_par_locate": (_i32, [_u64, _u64, _u64, _u64p, _u64p]),
+    "smb200_par_create": (_i32, [_p, _u64, _u64, _i32, _i32, _pp]),
+    "smb200_par_free": (_i32, [_p]),
+    "smb200_par_owner": (_i32, [_p, _u64, C.POINTER(_i32)]),
+    "smb200_par_set_block_indexlist": (_i32, [_p, _u64, _u64, _u64, _u64, _p, _p, _p, _p]),
+    "smb200_par_set_block_crs": (_i32, [_p, _u64, _u64, _u64, _u64, _p, _p, _p]),
+    "smb200_par_dims": (_i32, [_p, _u64p]),
+    "smb200_par_block": (_i32, [_p, _u64, _pp]),
+    "smb200_par_mvp": (_i32, [_p, _p, _p]),
     "smb200_partition_rows": (_i32, [_u64, C.c_uint32, _u64, _u64p]),
     "smb200_partition_rows_by_nnz": (_i32, [_i32, _u64, _p, C.c_uint32, _u64p]),
     "smb200_ghost_plan": (_i32, [_i32, _u64, _p, C.c_uint32, C.c_uint32, _u64p, _p, _u64p, _u64p, _u64p]),

@@ -577,6 +577,19 @@ class JacobiPCG:
 
 
 # ---- partition contract + multi-GPU ---------------------------------------------------------------------------
+class _ParHandle:
+    def __init__(self, h):
+        self.h = h
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib.smb200_par_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
 class SparseMatPar:
     """sparsemat_par.rs:12-140: 1-D row blocks of R = max_n_rows / n_blocks rows, each a SparseMatIndexList with LOCAL
     row ids and GLOBAL column ids, assembled on the host like the reference.  ``mvp`` is the reference's commented-out
@@ -656,29 +669,36 @@ class SparseMatPar:
         return float(self.n_non_zero_entries()) / float(self.n_rows() * self.n_cols())
 
     def to_device(self, ctx: Context):
-        """to_crs() of every block on the GPU (bit-exact layout per block)."""
-        self._device = (ctx, [m.to_crs(ctx) for m in self.sub_matrices])
+        """The device container (smb200_par_*): to_crs() of every block on its owner's GPU, bit-exact layout per block.  With a
+        communicator on the context, block b lives on rank b * world / n_blocks and every rank makes this same call."""
+        h = C.c_void_p()
+        check(lib.smb200_par_create(ctx._h, self.n_blocks, self.max_n_rows, F.vtype_of(self.dtype), F.itype_of(self.itype), C.byref(h)))
+        dev = _ParHandle(h)
+        for b, m in enumerate(self.sub_matrices):
+            r, c, z = m._dims()
+            cols, vals, pos, nxt = m.raw_arrays()
+            check(lib.smb200_par_set_block_indexlist(h, b, r, c, z, F.ptr(cols), F.ptr(vals), F.ptr(pos), F.ptr(nxt)))
+        self._device = (ctx, dev)
         return self
 
+    def owner(self, block_id: int) -> int:
+        """Rank that holds block `block_id` on the device (after to_device)."""
+        r = C.c_int32()
+        check(lib.smb200_par_owner(self._device[1].h, block_id, C.byref(r)))
+        return r.value
+
     def mvp(self, rhs: DenseVec) -> DenseVec:
-        """y = A x, block by block against the shared x (the `Arc<rhs>` of sparsemat_par.rs:40-42)."""
+        """y = A x: the completed mvp_par (sparsemat_par.rs:37-68) — every device multiplies its blocks against the shared x
+        (the `Arc<rhs>`), the slices of y are gathered on every rank."""
         ctx = rhs.ctx
         if self._device is None or self._device[0] is not ctx:
             self.to_device(ctx)
-        n = self.n_rows()
-        y = DenseVec(ctx, n, self.dtype)
-        R = self.n_rows_sub_matrix
-        done = 0
-        for b, crs in enumerate(self._device[1]):
-            rows_b = crs.n_rows()
-            if rows_b == 0 or done >= n:
-                break
-            if b * R + rows_b < n and rows_b < R:
-                # the default mvp would call IndexList::iter_row past the block's last row (indexlist.rs:88)
-                raise Panic("index out of bounds")
-            view = DenseVec.wrap(ctx, y.device_ptr() + b * R * self.dtype.itemsize, rows_b, self.dtype)
-            crs.mvp(rhs, out=view)
-            done = b * R + rows_b
+        y = DenseVec(ctx, self.n_rows(), self.dtype)
+        st = lib.smb200_par_mvp(self._device[1].h, rhs._h, y._h)
+        if st == F.ERR_INVALID and "index out of bounds" in F.last_error():
+            # the default mvp would call IndexList::iter_row past a short block's last row (indexlist.rs:88)
+            raise Panic("index out of bounds")
+        check(st)
         return y
 
     def __mul__(self, rhs):

@@ -42,6 +42,7 @@ struct NcclApi {
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
@@ -70,6 +71,7 @@ static smb200_status nccl_load() {
     LOAD(CommDestroy, "ncclCommDestroy");
     LOAD(AllReduce, "ncclAllReduce");
     LOAD(AllGather, "ncclAllGather");
+    LOAD(Broadcast, "ncclBroadcast");
     LOAD(Send, "ncclSend");
     LOAD(Recv, "ncclRecv");
     LOAD(GroupStart, "ncclGroupStart");
@@ -87,6 +89,15 @@ static smb200_status nccl_load() {
     } while (0)
 
 static int nccl_vtype(int vt) { return vt == SMB200_F64 ? kNcclFloat64 : kNcclFloat32; }
+
+// for par.cu (SparseMatPar's gather of y)
+smb200_status nccl_group_begin() { SMB_TRY(nccl_load()); SMB_NCCL(g_nccl.GroupStart()); return SMB200_OK; }
+smb200_status nccl_group_end() { SMB_NCCL(g_nccl.GroupEnd()); return SMB200_OK; }
+smb200_status nccl_bcast_bytes(smb200_ctx* ctx, void* buf, size_t bytes, int root, cudaStream_t stream) {
+    SMB_REQUIRE(ctx->comm, SMB200_ERR_INVALID, "call smb200_comm_init first");
+    SMB_NCCL(g_nccl.Broadcast(buf, buf, bytes, kNcclUint8, root, (ncclComm_t)ctx->comm, stream));
+    return SMB200_OK;
+}
 
 template <class T>
 __global__ void pack_kernel(const T* __restrict__ x, const uint64_t* __restrict__ idx, uint64_t n, T* __restrict__ out) {

@@ -113,6 +113,25 @@ def _worker(rank, world, port, out_q, path):
             inf = a.info()
             assert not inf["peer_timeout"] and (path != "p2p" or inf["products"] == 5), inf
             a.barrier()
+        # ---- (4) SparseMatPar with a working mvp_par (sparsemat_par.rs:37-68): 6 blocks on `world` GPUs, replicated x, the
+        #          slices of y gathered on every rank; the last block is short (and an empty one follows) ----------------------
+        if path == "p2p":
+            n_rows, n_cols, vals, cols, offs = cases.ragged(71, 1100, 900, 11, np.float64, np.uint32, empty_frac=0.0)
+            i = np.repeat(np.arange(n_rows), np.diff(offs.astype(np.int64)))
+            keep = i < 1100 - 150                                        # rows 950.. stay empty: block 4 holds 150 of 200 rows, block 5 none
+            edge = np.arange(0, 800, 200) + 199                          # make sure blocks 0..3 are full (their last row exists)
+            ii, jj, vv = np.append(i[keep], edge), np.append(cols[keep], np.zeros(4, np.uint32)), np.append(vals[keep], np.full(4, 0.25))
+            ii, jj, vv = np.append(ii, 949), np.append(jj, 1), np.append(vv, 0.5)
+            par = smb.SparseMatPar(6, 1200, np.float64, np.uint32)
+            par.set(ii, jj, vv)
+            ref = orc.IndexListMat(np.float64, np.uint32)
+            ref.set(ii, jj, vv)
+            _, _, wv, wc, wo = ref.to_crs()
+            xg = orc.uniform(np.float64, 9, 900)
+            y = par.mvp(smb.DenseVec.from_vec(ctx, xg))
+            assert par.n_rows() == 950 and y.dim() == 950
+            assert len({par.owner(b) for b in range(6)}) == min(world, 6)            # the blocks are spread over the ranks
+            assert np.array_equal(y.to_numpy(), orc.mvp(wv, wc, wo, xg)), "SparseMatPar mvp_par over the ranks is not bit-exact"
         ctx.sync()
         dist.barrier()
         dist.destroy_process_group()
