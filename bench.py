@@ -517,7 +517,10 @@ def run_ours(args):
                         else "K products, CUDA events on the library stream",
     }
     if multi:
-        line["dist"] = {"data_path": "peer memory over NVLink (CUDA IPC): halo planes stored by the product kernel, no NCCL call per step"
+        di = a.info() if a is not None else dist_info
+        line["dist"] = {"halo_wait_avg_us_rank0": (di["wait_ns_total"] / di["waits"] / 1e3) if di["waits"] else 0.0,
+                        "halo_waits_per_product_rank0": di["waits"] / max(1, di["products"]),
+                        "data_path": "peer memory over NVLink (CUDA IPC): halo planes stored by the product kernel, no NCCL call per step"
                                      if dist_info["p2p"] else "NCCL send/recv fallback",
                         "neighbours_rank0": dist_info["neighbours"], "halo_elems_rank0": int(n_ghost)}
 

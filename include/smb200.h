@@ -341,9 +341,10 @@ smb200_status smb200_dist_dot(smb200_dist* d, const smb200_vec* x, const smb200_
 /* Stream-ordered barrier over the ranks (no host synchronisation): work queued behind it on the
  * context stream starts only after every rank's stream has reached its own barrier. */
 smb200_status smb200_dist_barrier(smb200_dist* d);
-/* out4 = {1 if the peer-memory path is active (0: NCCL fallback), halo neighbours of this rank,
- * distributed products completed, 1 if a peer wait timed out}.  Synchronises the context stream. */
-smb200_status smb200_dist_info(smb200_dist* d, uint64_t* out4);
+/* out6 = {1 if the peer-memory path is active (0: NCCL fallback), halo neighbours of this rank,
+ * distributed products completed, 1 if a peer wait timed out, sum of the spin times of all threads that
+ * waited for a neighbour's flag in ns, number of such waits}.  Synchronises the context stream. */
+smb200_status smb200_dist_info(smb200_dist* d, uint64_t* out6);
 smb200_status smb200_dist_cg_solve(smb200_dist* d, const smb200_vec* b, smb200_vec* x, double tol, int32_t relative,
                                    uint64_t iter_max, smb200_cg_stats* stats);
 

@@ -174,7 +174,7 @@ extern "C" {
     pub fn smb200_dist_spmv(d: *mut smb200_dist, x: *mut smb200_vec, y: *mut smb200_vec) -> smb200_status;
     pub fn smb200_dist_dot(d: *mut smb200_dist, x: *const smb200_vec, y: *const smb200_vec, out: *mut f64) -> smb200_status;
     pub fn smb200_dist_barrier(d: *mut smb200_dist) -> smb200_status;
-    pub fn smb200_dist_info(d: *mut smb200_dist, out4: *mut u64) -> smb200_status;
+    pub fn smb200_dist_info(d: *mut smb200_dist, out6: *mut u64) -> smb200_status;
     pub fn smb200_dist_cg_solve(d: *mut smb200_dist, b: *const smb200_vec, x: *mut smb200_vec, tol: f64, relative: i32,
                                 iter_max: u64, stats: *mut smb200_cg_stats) -> smb200_status;
 }

@@ -800,6 +800,7 @@ class DistCRS:
         check(lib.smb200_dist_barrier(self._h))
 
     def info(self) -> dict:
-        d = (C.c_uint64 * 4)()
+        d = (C.c_uint64 * 6)()
         check(lib.smb200_dist_info(self._h, d))
-        return {"p2p": bool(d[0]), "neighbours": int(d[1]), "products": int(d[2]), "peer_timeout": bool(d[3])}
+        return {"p2p": bool(d[0]), "neighbours": int(d[1]), "products": int(d[2]), "peer_timeout": bool(d[3]),
+                "wait_ns_total": int(d[4]), "waits": int(d[5])}

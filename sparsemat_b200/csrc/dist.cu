@@ -288,6 +288,7 @@ static smb200_status dist_p2p_setup(smb200_dist* d) {
         h.epoch = (unsigned long long*)(misc + 0);
         h.ctr = (unsigned*)(misc + 16);
         h.error = (unsigned*)(misc + 24);
+        h.wait_stats = (unsigned long long*)(misc + 32);
         h.flags = (unsigned long long*)d->win;
         h.ghost = (unsigned char*)d->win + 256;
         h.ghost_stride = 64;
@@ -371,6 +372,7 @@ static smb200_status dist_p2p_setup(smb200_dist* d) {
     h.epoch = (unsigned long long*)(misc + 0);
     h.ctr = (unsigned*)(misc + 16);
     h.error = (unsigned*)(misc + 24);
+    h.wait_stats = (unsigned long long*)(misc + 32);
     h.flags = (unsigned long long*)((unsigned char*)d->win + L.flags);
     h.ghost = (unsigned char*)d->win + L.ghost;
     h.ghost_stride = stride;
@@ -878,20 +880,19 @@ smb200_status smb200_dist_barrier(smb200_dist* d) {
     return SMB200_OK;
 }
 
-smb200_status smb200_dist_info(smb200_dist* d, uint64_t* out4) {
-    SMB_REQUIRE(d && out4, SMB200_ERR_INVALID, "dist_info: NULL argument");
-    out4[0] = d->p2p ? 1 : 0;
-    out4[1] = (uint64_t)d->n_nbr;
-    out4[2] = 0;
-    out4[3] = 0;
+smb200_status smb200_dist_info(smb200_dist* d, uint64_t* out6) {
+    SMB_REQUIRE(d && out6, SMB200_ERR_INVALID, "dist_info: NULL argument");
+    out6[0] = d->p2p ? 1 : 0;
+    out6[1] = (uint64_t)d->n_nbr;
+    out6[2] = out6[3] = out6[4] = out6[5] = 0;
     if (d->p2p) {
         SMB_CUDA(cudaStreamSynchronize(d->ctx->stream));
-        unsigned long long ep = 0;
-        unsigned err = 0;
-        SMB_CUDA(cudaMemcpy(&ep, d->misc, sizeof ep, cudaMemcpyDeviceToHost));
-        SMB_CUDA(cudaMemcpy(&err, (unsigned char*)d->misc + 24, sizeof err, cudaMemcpyDeviceToHost));
-        out4[2] = ep;
-        out4[3] = err;
+        unsigned long long words[6] = {0, 0, 0, 0, 0, 0};            // misc: epoch, all-reduce epoch, counters, error, wait ns, waits
+        SMB_CUDA(cudaMemcpy(words, d->misc, sizeof words, cudaMemcpyDeviceToHost));
+        out6[2] = words[0];
+        out6[3] = (uint64_t)(words[3] & 0xffffffffull);
+        out6[4] = words[4];
+        out6[5] = words[5];
     }
     return SMB200_OK;
 }

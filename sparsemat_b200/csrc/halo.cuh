@@ -27,6 +27,7 @@ struct HaloDev {
     unsigned* ctr;                        // [2] arrivals: push finished / product finished; zero between launches (local)
     unsigned long long* flags;            // [world] flags[q] = last epoch rank q has pushed into this rank's buffer (peers write)
     unsigned* error;                      // [1] set when a wait ran into the timeout
+    unsigned long long* wait_stats;       // [2] evidence: {sum of the waiting threads' spin times in ns, number of waits}
     void* ghost;                          // this rank's ghost buffer: 2 halves of ghost_stride elements (peers write)
     unsigned long long ghost_stride;      // elements per half
     unsigned long long n_ghost;
@@ -114,6 +115,7 @@ __device__ __forceinline__ bool halo_wait(const HaloDev& h, unsigned long long e
             __nanosleep(40);
         }
     }
+    if (h.wait_stats) { atomicAdd(h.wait_stats, global_timer_ns() - t0); atomicAdd(h.wait_stats + 1, 1ull); }
     return true;
 }
 #endif
