@@ -117,6 +117,10 @@ typedef struct {
     uint64_t plan_bytes;      /* device memory the plan holds beside the three CRS arrays (split points, x windows,
                                * 16-bit columns / offsets, band parts)                                                */
     double plan_ms;           /* host wall-clock time the plan took to build (once per matrix and variant)            */
+    uint64_t nnz_v8;          /* RING: non-zeros whose value is streamed as an 8-bit code into the block's dictionary of
+                               * distinct values (plan-time value indexing: every block holds <= 256 distinct values —
+                               * constant-coefficient stencils, unit-weight graphs; same operands, bit-identical results);
+                               * stream_bytes then counts 1 byte per value plus one 256-entry dictionary per block      */
 } smb200_plan_info;
 
 typedef struct {

@@ -59,6 +59,7 @@ pub struct smb200_plan_info {
     pub rows_o16: u64,
     pub plan_bytes: u64,
     pub plan_ms: f64,
+    pub nnz_v8: u64,
 }
 
 #[repr(C)]

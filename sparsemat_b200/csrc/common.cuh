@@ -120,6 +120,9 @@ struct SpmvPlan {
     unsigned long long* seg_lo = nullptr; // RING: [4 * n_blocks] first column of each x segment of the block (aligned down)
     unsigned* seg_len = nullptr;        // RING: [4 * n_blocks] segment lengths in elements (0 = unused; all 0 = no window)
     unsigned ocap = 0, xcap = 0;        // RING: row-offset / x-window capacity of a stage (elements)
+    uint8_t* vcodes = nullptr;          // RING, value indexing: 8-bit code of every non-zero into its block's dictionary
+    void* vdict = nullptr;              //       [256 * n_blocks] dictionaries (T): the sorted distinct values of each block
+    uint64_t n_v8 = 0;                  //       non-zeros whose value the kernel reads through a code
     uint16_t* loffs = nullptr;          // RING, packed plans: 16-bit row offsets relative to each block's slice start
     uint64_t loffs_row_begin = 0;       //       first row of the plan's range (the kernel derives a block's position from it)
     uint64_t n_o16 = 0;                 //       rows whose offsets the kernel reads from loffs

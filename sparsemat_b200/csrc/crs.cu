@@ -394,6 +394,15 @@ smb200_status smb200_crs_scale(smb200_crs* m, double s) {
     else scale_values_kernel<float><<<g, 256, 0, m->ctx->stream>>>((float*)m->values, m->nnz, (float)s);
     count_launch();
     SMB_CUDA(cudaGetLastError());
+    // a value-indexed ring plan multiplies the blocks' dictionaries, not m->values: every dictionary entry takes the same
+    // single rounding as the value it stands for (range plans are never value-indexed, spmv.cu ring_plan)
+    if (m->plan.vdict && m->plan.n_blocks) {
+        const uint64_t nd = m->plan.n_blocks * 256;
+        if (m->vt == SMB200_F64) scale_values_kernel<double><<<g, 256, 0, m->ctx->stream>>>((double*)m->plan.vdict, nd, s);
+        else scale_values_kernel<float><<<g, 256, 0, m->ctx->stream>>>((float*)m->plan.vdict, nd, (float)s);
+        count_launch();
+        SMB_CUDA(cudaGetLastError());
+    }
     // a band-split plan multiplies its own copies of the values (bandsplit.cu): they are scaled with the matrix, so that
     // `scale` affects every later product as in the reference (sparsemat_crs.rs:153-157)
     for (smb200_crs* part : m->plan.parts) SMB_TRY(smb200_crs_scale(part, s));

@@ -29,6 +29,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <type_traits>
 #include <cstdlib>
 
 namespace smb {
@@ -42,7 +43,8 @@ constexpr unsigned kBlkNoFit = 1u;   // PIPE block flags: slice larger than a st
 constexpr unsigned kBlkLong = 2u;    //                   a row of more than kWarpRowMin entries -> two-pass row sums
 constexpr unsigned kBlkShort = 4u;   //                   every row has <= kRowMajorMax entries -> row-major path
 constexpr int kRowMajorMax = 32;
-constexpr int kRingRowMax = 256;     // RING: longest row it takes (8 lanes per row x 32 entries per lane)
+constexpr int kRingRowMax = 256;
+constexpr unsigned long long kSliceAlign = 16;   // RING: slices start / end at multiples of 16 entries (16 bytes of 8-bit value codes)     // RING: longest row it takes (8 lanes per row x 32 entries per lane)
 constexpr int kPipeMaxStages = 8;
 
 struct DotArgs {
@@ -913,11 +915,16 @@ __device__ __forceinline__ double ring_rows(const T* sv, const I* sc, const I* s
 // Same with compressed columns: the plan stored, for every non-zero of a windowed block, the 16-bit position of its
 // column inside the block's concatenated x windows, so a stage carries 2 bytes per column instead of sizeof(I) and the
 // consumer needs no window search.  The arithmetic (operands, order, roundings) is unchanged.
-template <class T, class I, bool DOT, bool O16, int LANES = 1>
+// V8 (value indexing): the plan found at most 256 distinct values in every block (constant-coefficient stencils, unit-weight
+// graphs) and stored one 8-bit code per non-zero plus the block's dictionary; the value area of the stage then holds the
+// codes and `dict` the values themselves.  Same operands in the same order: results do not change by a bit.
+template <class T, class I, bool DOT, bool O16, int LANES = 1, bool V8 = false>
 __device__ __forceinline__ double ring_rows_c16(const T* sv, const uint16_t* sc, const I* so, const T* sx, const RingDesc& d,
-                                                unsigned lane_id, unsigned n_lanes, T* __restrict__ y, const T* __restrict__ w) {
+                                                unsigned lane_id, unsigned n_lanes, T* __restrict__ y, const T* __restrict__ w,
+                                                const T* dict = nullptr) {
     const uint64_t r0 = d.r0, r1 = d.r1, a0 = d.a0, r0a = d.r0a;
     double acc = 0.0;
+    [[maybe_unused]] const uint8_t* vc = reinterpret_cast<const uint8_t*>(sv);
     if constexpr (LANES > 1) {
         // Rows of 33..256 entries (FEM with several unknowns per node): LANES consecutive threads share a row, lane l sums the
         // entries l, l + LANES, ... (consecutive shared-memory words across the group), a fixed xor-shuffle tree adds the
@@ -947,7 +954,10 @@ __device__ __forceinline__ double ring_rows_c16(const T* sv, const uint16_t* sc,
             if constexpr (DOT) wv = __ldg(w + r);
             T sum = T(0);
 #pragma unroll 4
-            for (unsigned k = ka; k < ke; ++k) sum = add_rn(sum, mul_rn(sx[sc[k]], sv[k]));
+            for (unsigned k = ka; k < ke; ++k) {
+                if constexpr (V8) sum = add_rn(sum, mul_rn(sx[sc[k]], dict[vc[k]]));
+                else sum = add_rn(sum, mul_rn(sx[sc[k]], sv[k]));
+            }
             y[r] = sum;
             if constexpr (DOT) acc += (double)mul_rn(wv, sum);
         }
@@ -960,14 +970,16 @@ struct NoHalo {};
 template <bool DIST> struct HaloParam { using type = NoHalo; };
 template <> struct HaloParam<true> { using type = HaloDev; };       // by value: its fields are read from the constant bank
 // LANES = threads per row of the compressed-column path: 1 (rows <= 32 entries, storage-order sums, bit-exact) or 2 / 4 / 8.
-template <class T, class I, bool DOT, bool DIST, int LANES>
+// V8 = the stage's value area holds 8-bit codes into the block's dictionary (plan-time value indexing; LANES = 1 only).
+template <class T, class I, bool DOT, bool DIST, int LANES, bool V8>
 __global__ void __launch_bounds__(kRingThreads, 2)
 spmv_ring_kernel(const T* __restrict__ vals, const I* __restrict__ cols, const I* __restrict__ offs,
                  const I* __restrict__ blk_rows, const I* __restrict__ blk_nnz, const unsigned long long* __restrict__ seg_lo,
                  const unsigned* __restrict__ seg_len, unsigned n_blocks, unsigned cap, unsigned ocap, unsigned xcap,
                  unsigned colb, unsigned stages, int xwin_ok, const uint16_t* __restrict__ lcols, unsigned long long lcols_base,
                  const uint16_t* __restrict__ loffs, unsigned long long row_begin, const T* __restrict__ x, T* __restrict__ y,
-                 DotArgs dot, const typename HaloParam<DIST>::type halo, unsigned rot) {
+                 DotArgs dot, const typename HaloParam<DIST>::type halo, unsigned rot, const uint8_t* __restrict__ vcodes,
+                 const T* __restrict__ vdict) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full[kPipeMaxStages];    // producer -> consumers: the stage's bytes have landed
     __shared__ __align__(8) uint64_t empty[kPipeMaxStages];   // consumers -> producer: every consumer warp has left the stage
@@ -975,10 +987,11 @@ spmv_ring_kernel(const T* __restrict__ vals, const I* __restrict__ cols, const I
     constexpr unsigned OA = 16 / sizeof(I);
     constexpr unsigned kConsumerWarps = kRingThreads / 32 - 1;
     const unsigned tid = threadIdx.x;
-    const size_t o_cols = (size_t)cap * sizeof(T);
+    const size_t o_cols = (size_t)cap * (V8 ? 1 : sizeof(T));  // V8: one code byte per entry (cap is a multiple of 16)
     const size_t o_offs = o_cols + (size_t)cap * colb;          // colb = 2: every block of the plan streams 16-bit columns
     const size_t o_x = o_offs + (size_t)(ocap + 8) * (loffs ? 2 : sizeof(I));   // loffs: ocap is a multiple of 8
-    const size_t stage_bytes = o_x + (size_t)xcap * sizeof(T);
+    const size_t o_dict = o_x + (size_t)xcap * sizeof(T);
+    const size_t stage_bytes = o_dict + (V8 ? 256 * sizeof(T) : 0);
     double stop = 0.0;
     if constexpr (DOT) { if (dot.done != nullptr) stop = __ldcg(dot.done); }
     if (stop != 0.0) return;
@@ -1033,9 +1046,9 @@ spmv_ring_kernel(const T* __restrict__ vals, const I* __restrict__ cols, const I
                 if (j >= stages) mbar_wait(&empty[s], parity ^ 1u);     // the consumers have drained this stage's previous block
                 RingDesc& d = s_desc[s];
                 unsigned char* base = smem_raw + (size_t)s * stage_bytes;
-                // slices start at a multiple of 8 elements: 16-byte aligned for 2-byte compressed columns as well
-                const unsigned long long a0 = n0 & ~7ull, r0a = r0 & ~(unsigned long long)(OA - 1);
-                const unsigned count = (unsigned)(((n1 - a0) + 7ull) & ~7ull);
+                // slices start at a multiple of 16 elements: 16-byte aligned for 1-byte value codes and 2-byte columns as well
+                const unsigned long long a0 = n0 & ~(kSliceAlign - 1), r0a = r0 & ~(unsigned long long)(OA - 1);
+                const unsigned count = (unsigned)(((n1 - a0) + (kSliceAlign - 1)) & ~(kSliceAlign - 1));
                 // row offsets: full width from the CRS array, or the plan's 16-bit copy (block b's entries start at a multiple of 8)
                 const bool o16 = loffs != nullptr;
                 const unsigned ocount = o16 ? (unsigned)(((r1 - r0 + 1) + 7ull) & ~7ull)
@@ -1057,8 +1070,9 @@ spmv_ring_kernel(const T* __restrict__ vals, const I* __restrict__ cols, const I
                 d.xwin = xw ? nseg : 0u;
                 d.c16 = c16 ? 1u : 0u;
                 const unsigned cbytes = count * (c16 ? 2u : (unsigned)sizeof(I));
-                unsigned bytes = count * (unsigned)sizeof(T) + cbytes + obytes;
+                unsigned bytes = count * (unsigned)(V8 ? 1 : sizeof(T)) + cbytes + obytes;
                 if (xw) bytes += xtotal * (unsigned)sizeof(T);
+                if constexpr (V8) bytes += 256u * (unsigned)sizeof(T);
                 if constexpr (DIST) {
                     // A block without windows gathers any column, a windowed one needs the ghosts if a window reaches past g0;
                     // and a product ends only after every neighbour's flag of its epoch was seen (halo.cuh, step 3): CTA 0
@@ -1071,10 +1085,12 @@ spmv_ring_kernel(const T* __restrict__ vals, const I* __restrict__ cols, const I
                 }
                 mbar_expect_tx(&full[s], bytes);
                 if (count) {
-                    bulk_g2s(base, vals + a0, count * (unsigned)sizeof(T), &full[s]);
+                    if constexpr (V8) bulk_g2s(base, vcodes + (a0 - lcols_base), count, &full[s]);
+                    else bulk_g2s(base, vals + a0, count * (unsigned)sizeof(T), &full[s]);
                     if (c16) bulk_g2s(base + o_cols, lcols + (a0 - lcols_base), cbytes, &full[s]);
                     else bulk_g2s(base + o_cols, cols + a0, cbytes, &full[s]);
                 }
+                if constexpr (V8) bulk_g2s(base + o_dict, vdict + 256 * b, 256u * (unsigned)sizeof(T), &full[s]);
                 if (o16) bulk_g2s(base + o_offs, loffs + (((r0 - row_begin) + 8ull * b) & ~7ull), obytes, &full[s]);
                 else bulk_g2s(base + o_offs, offs + r0a, obytes, &full[s]);
                 if (xw) {
@@ -1121,11 +1137,12 @@ spmv_ring_kernel(const T* __restrict__ vals, const I* __restrict__ cols, const I
             const I* so = reinterpret_cast<const I*>(base + o_offs);
             const T* sx = reinterpret_cast<const T*>(base + o_x);
             const T* w = (const T*)dot.w;
-            if (d.c16) {
+            if (V8 || d.c16) {                    // (a V8 plan is packed: every block streams compressed columns)
                 const uint16_t* sc16 = reinterpret_cast<const uint16_t*>(base + o_cols);
-                if (d.o16) acc += ring_rows_c16<T, I, DOT, true, LANES>(sv, sc16, so, sx, d, lane_id, n_lanes, y, w);
-                else acc += ring_rows_c16<T, I, DOT, false, LANES>(sv, sc16, so, sx, d, lane_id, n_lanes, y, w);
-            } else switch (d.xwin) {              // number of x windows of the block (block-uniform)
+                const T* dict = reinterpret_cast<const T*>(base + o_dict);
+                if (d.o16) acc += ring_rows_c16<T, I, DOT, true, LANES, V8>(sv, sc16, so, sx, d, lane_id, n_lanes, y, w, dict);
+                else acc += ring_rows_c16<T, I, DOT, false, LANES, V8>(sv, sc16, so, sx, d, lane_id, n_lanes, y, w, dict);
+            } else if constexpr (!V8) switch (d.xwin) {              // number of x windows of the block (block-uniform)
                 case 0:
                     if (d.o16) acc += ring_rows<T, I, DOT, 0, true, DIST>(sv, sc, so, sx, d, lane_id, n_lanes, x, y, w, gx, g0);
                     else acc += ring_rows<T, I, DOT, 0, false, DIST>(sv, sc, so, sx, d, lane_id, n_lanes, x, y, w, gx, g0);
@@ -1271,6 +1288,76 @@ ring_compress_kernel(const I* __restrict__ cols, const I* __restrict__ blk_nnz, 
     if (threadIdx.x == 0) atomicAdd(n_c16, (unsigned long long)(n1 - n0));
 }
 
+// Plan time, one CTA per block: value indexing.  The block's distinct values (bit patterns) are collected in a shared-memory
+// hash set; with at most 256 of them the sorted set becomes the block's dictionary and every non-zero gets its 8-bit code.
+// A block with more distinct values raises *n_fail (the plan then keeps full-width values).  probe_only: count only.
+template <class T, class I>
+__global__ void __launch_bounds__(256)
+ring_vdict_kernel(const T* __restrict__ vals, const I* __restrict__ blk_nnz, unsigned long long codes_base, uint8_t* __restrict__ codes,
+                  T* __restrict__ dicts, unsigned long long* __restrict__ n_fail, int probe_only) {
+    using U = typename std::conditional<sizeof(T) == 8, unsigned long long, unsigned>::type;
+    constexpr unsigned kSlots = 1024;
+    constexpr U kEmpty = ~(U)0;                       // (a NaN pattern; a value with exactly these bits is kept in s_has_empty)
+    __shared__ U slots[kSlots];
+    __shared__ U dict[256];
+    __shared__ unsigned s_count, s_over, s_has_empty;
+    const size_t b = blockIdx.x;
+    const uint64_t n0 = (uint64_t)blk_nnz[b], n1 = (uint64_t)blk_nnz[b + 1];
+    for (unsigned i = threadIdx.x; i < kSlots; i += 256) slots[i] = kEmpty;
+    if (threadIdx.x == 0) { s_count = 0; s_over = 0; s_has_empty = 0; }
+    __syncthreads();
+    for (uint64_t k = n0 + threadIdx.x; k < n1 && !s_over; k += 256) {
+        U bits;
+        const T v = vals[k];
+        memcpy(&bits, &v, sizeof bits);
+        if (bits == kEmpty) { s_has_empty = 1; continue; }
+        unsigned h = (unsigned)((bits * (U)0x9E3779B97F4A7C15ull) >> (sizeof(U) * 8 - 10));
+        for (unsigned probe = 0; probe < kSlots; ++probe, h = (h + 1) & (kSlots - 1)) {
+            const U old = atomicCAS(&slots[h], kEmpty, bits);
+            if (old == bits) break;
+            if (old == kEmpty) { if (atomicAdd(&s_count, 1u) >= 256u) s_over = 1; break; }
+        }
+    }
+    __syncthreads();
+    const unsigned distinct = s_count + s_has_empty;
+    if (s_over || distinct > 256u) { if (threadIdx.x == 0) atomicAdd(n_fail, 1ull); return; }
+    if (probe_only) return;
+    // compact the set and sort it by bit pattern (rank by counting: <= 256 elements, one thread each)
+    __shared__ U found[256];
+    __shared__ unsigned s_nf;
+    if (threadIdx.x == 0) s_nf = 0;
+    __syncthreads();
+    for (unsigned i = threadIdx.x; i < kSlots; i += 256)
+        if (slots[i] != kEmpty) found[atomicAdd(&s_nf, 1u)] = slots[i];
+    __syncthreads();
+    if (threadIdx.x == 0 && s_has_empty) found[s_nf++] = kEmpty;
+    __syncthreads();
+    const unsigned nf = s_nf;
+    dict[threadIdx.x] = 0;
+    __syncthreads();
+    if (threadIdx.x < nf) {
+        const U mine = found[threadIdx.x];
+        unsigned rank = 0;
+        for (unsigned i = 0; i < nf; ++i) rank += found[i] < mine ? 1u : 0u;      // distinct values: ranks are a permutation
+        dict[rank] = mine;
+    }
+    __syncthreads();
+    {
+        T v;
+        const U bits = dict[threadIdx.x];
+        memcpy(&v, &bits, sizeof v);
+        dicts[256 * b + threadIdx.x] = v;
+    }
+    for (uint64_t k = n0 + threadIdx.x; k < n1; k += 256) {
+        U bits;
+        const T v = vals[k];
+        memcpy(&bits, &v, sizeof bits);
+        unsigned lo = 0, hi = nf;                       // first index with dict[i] >= bits
+        while (lo < hi) { const unsigned mid = (lo + hi) >> 1; if (dict[mid] < bits) lo = mid + 1; else hi = mid; }
+        codes[k - codes_base] = (uint8_t)lo;
+    }
+}
+
 // Plan time, one CTA per block: 16-bit row offsets relative to the start of the block's slice (a0 = blk_nnz[b] & ~7).
 // Block b's rows + 1 entries start at ((r0 - row_begin) + 8 b) & ~7, a multiple of 8 entries (16 bytes) that never
 // reaches into the previous block's entries.
@@ -1280,7 +1367,7 @@ ring_offsets16_kernel(const I* __restrict__ offs, const I* __restrict__ blk_rows
                       unsigned long long row_begin, uint16_t* __restrict__ loffs) {
     const unsigned long long b = blockIdx.x;
     const unsigned long long r0 = (unsigned long long)blk_rows[b], r1 = (unsigned long long)blk_rows[b + 1];
-    const unsigned long long a0 = (unsigned long long)blk_nnz[b] & ~7ull;
+    const unsigned long long a0 = (unsigned long long)blk_nnz[b] & ~(kSliceAlign - 1);
     const unsigned long long base = ((r0 - row_begin) + 8ull * b) & ~7ull;
     for (unsigned long long i = threadIdx.x; i <= r1 - r0; i += 128) loffs[base + i] = (uint16_t)((unsigned long long)offs[r0 + i] - a0);
 }
@@ -1392,6 +1479,8 @@ void plan_free(SpmvPlan& p) {
     if (p.seg_len) cudaFree(p.seg_len);
     if (p.lcols) cudaFree(p.lcols);
     if (p.loffs) cudaFree(p.loffs);
+    if (p.vcodes) cudaFree(p.vcodes);
+    if (p.vdict) cudaFree(p.vdict);
     if (p.blk_win) cudaFree(p.blk_win);
     for (smb200_crs* part : p.parts) smb200_crs_free(part);
     p = SpmvPlan();
@@ -1486,6 +1575,7 @@ static uint64_t plan_device_bytes(const smb200_crs* m, const SpmvPlan& p) {
     if (p.seg_len) b += (uint64_t)kNSeg * p.n_blocks * 4;
     if (p.lcols) b += (p.n_c16 ? p.n_c16 : m->nnz) * 2 + kPadBytes;
     if (p.loffs) b += (p.n_o16 + 8 * p.n_blocks + 16) * 2 + kPadBytes;
+    if (p.vcodes) b += p.n_v8 + kPadBytes + p.n_blocks * 256 * vsize(m->vt);
     if (p.blk_win) b += 2 * p.n_blocks * is;
     for (const smb200_crs* part : p.parts)
         b += part->nnz * (vsize(part->vt) + isize(part->it)) + (part->n_rows + 1) * isize(part->it) + plan_device_bytes(part, part->plan);
@@ -1575,7 +1665,7 @@ __global__ void block_extent_kernel(const I* __restrict__ blk_rows, const I* __r
     unsigned long long z = 0, r = 0;
     if (b < n_blocks) {
         const unsigned long long n0 = (unsigned long long)blk_nnz[b], n1 = (unsigned long long)blk_nnz[b + 1];
-        z = ((n1 + 7ull) & ~7ull) - (n0 & ~7ull);
+        z = ((n1 + (kSliceAlign - 1)) & ~(kSliceAlign - 1)) - (n0 & ~(kSliceAlign - 1));
         r = (unsigned long long)blk_rows[b + 1] - (unsigned long long)blk_rows[b];
     }
 #pragma unroll
@@ -1603,10 +1693,13 @@ static smb200_status ring_plan(smb200_crs* m, SpmvPlan& p, uint64_t rb, uint64_t
     const bool want_c16 = env_int("SMB200_RING_C16", 1) != 0;
     const bool want_o16 = env_int("SMB200_RING_O16", 1) != 0;
     bool packed = false;
-    if (want_c16 && nnz > 0 && env_int("SMB200_RING_PACK", 1) != 0 && getenv("SMB200_RING_CAP") == nullptr) {
+    // (a) with `vb` bytes per value in a stage (sizeof T, or 1 with value indexing) and `extra` more bytes per stage (the dictionary)
+    auto try_packed = [&](size_t vb, size_t extra) -> smb200_status {
+        packed = false;
+        const size_t budget = kRingStageBudget - extra;
         const double mean = (double)nnz / (double)rows;
-        const double bytes_per_key = (mean * (double)(ts + 2) + (double)is) / (mean + 2.0);
-        double t = (double)env_int("SMB200_RING_FILL", 70) * 0.01 * (double)kRingStageBudget / bytes_per_key;
+        const double bytes_per_key = (mean * (double)(vb + 2) + (double)is) / (mean + 2.0);
+        double t = (double)env_int("SMB200_RING_FILL", 70) * 0.01 * (double)budget / bytes_per_key;
         unsigned long long* d_ext = nullptr;
         SMB_CUDA(cudaMalloc(&d_ext, 2 * sizeof(unsigned long long)));
         for (int attempt = 0; attempt < 5 && !packed; ++attempt, t *= 0.9) {
@@ -1623,10 +1716,10 @@ static smb200_status ring_plan(smb200_crs* m, SpmvPlan& p, uint64_t rb, uint64_t
             cudaError_t e = cudaMemcpyAsync(h_ext, d_ext, sizeof h_ext, cudaMemcpyDeviceToHost, ctx->stream);
             if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
             if (e != cudaSuccess) { cudaFree(d_ext); SMB_CUDA(e); }
-            const size_t cap = (size_t)((h_ext[0] + 7ull) & ~7ull), ocap = (size_t)((h_ext[1] + 7ull) & ~7ull);
-            const size_t fixed = cap * (ts + 2) + (ocap + 8) * (want_o16 && cap + 16 < 65536 ? 2 : is);
-            if (fixed + 64 * ts > kRingStageBudget) continue;
-            size_t xc = (kRingStageBudget - fixed) / ts;
+            const size_t cap = (size_t)((h_ext[0] + (kSliceAlign - 1)) & ~(kSliceAlign - 1)), ocap = (size_t)((h_ext[1] + 7ull) & ~7ull);
+            const size_t fixed = cap * (vb + 2) + (ocap + 8) * (want_o16 && cap + 16 < 65536 ? 2 : is);
+            if (fixed + 64 * ts > budget) continue;
+            size_t xc = (budget - fixed) / ts;
             if (xc > 65536) xc = 65536;
             p.cap = (unsigned)cap;
             p.ocap = (unsigned)ocap;
@@ -1636,7 +1729,48 @@ static smb200_status ring_plan(smb200_crs* m, SpmvPlan& p, uint64_t rb, uint64_t
             packed = p.n_xwin == p.n_blocks;
         }
         cudaFree(d_ext);
+        return SMB200_OK;
+    };
+    auto vdict_run = [&](int probe_only, unsigned n_blk, unsigned long long* h_fail) -> smb200_status {
+        unsigned long long* d_fail = nullptr;
+        SMB_CUDA(cudaMalloc(&d_fail, sizeof(unsigned long long)));
+        cudaMemsetAsync(d_fail, 0, sizeof(unsigned long long), ctx->stream);
+#define SMB_VDICT(T, I) ring_vdict_kernel<T, I><<<n_blk, 256, 0, ctx->stream>>>((const T*)m->values, (const I*)p.blk_nnz, p.lcols_base, p.vcodes, (T*)p.vdict, d_fail, probe_only)
+        if (m->vt == SMB200_F64) { if (m->it == SMB200_U64) SMB_VDICT(double, uint64_t); else SMB_VDICT(double, uint32_t); }
+        else { if (m->it == SMB200_U64) SMB_VDICT(float, uint64_t); else SMB_VDICT(float, uint32_t); }
+#undef SMB_VDICT
+        count_launch();
+        cudaError_t e = cudaMemcpyAsync(h_fail, d_fail, sizeof *h_fail, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        cudaFree(d_fail);
+        SMB_CUDA(e);
+        return SMB200_OK;
+    };
+    const bool pack_ok = want_c16 && nnz > 0 && env_int("SMB200_RING_PACK", 1) != 0 && getenv("SMB200_RING_CAP") == nullptr;
+    // Value indexing (whole-matrix plans of one-lane ring kernels): if the first block-sized stretch of values has few distinct
+    // ones, cut the blocks for 1-byte values, then give every block its dictionary; any block with more than 256 distinct
+    // values sends the plan back to full-width values.
+    bool v8 = false;
+    if (pack_ok && want_o16 && rb == 0 && re == m->n_rows && p.lanes <= 1 && env_int("SMB200_RING_V8", 1) != 0) {
+        SMB_TRY(try_packed(1, 256 * ts));
+        if (packed && (size_t)p.cap + 16 < 65536) {
+            p.lcols_base = ob & ~(kSliceAlign - 1);
+            unsigned long long fails = 0;
+            SMB_TRY(vdict_run(1, (unsigned)std::min<uint64_t>(p.n_blocks, 64), &fails));      // probe: the first blocks only
+            if (fails == 0) {
+                const size_t n_c = (size_t)(oe - p.lcols_base) + kSliceAlign;
+                SMB_CUDA(cudaMalloc(&p.vcodes, n_c + kPadBytes));
+                SMB_CUDA(cudaMalloc(&p.vdict, p.n_blocks * 256 * ts));
+                cudaMemsetAsync(p.vcodes, 0, n_c + kPadBytes, ctx->stream);
+                SMB_TRY(vdict_run(0, (unsigned)p.n_blocks, &fails));
+                v8 = fails == 0;
+                if (!v8) { cudaFree(p.vcodes); cudaFree(p.vdict); p.vcodes = nullptr; p.vdict = nullptr; }
+            }
+        }
+        if (!v8) packed = false;
+        else p.n_v8 = nnz;
     }
+    if (!packed && pack_ok) SMB_TRY(try_packed(ts, 0));
     p.colb = packed ? 2u : (unsigned)is;
     if (!packed) {
         p.cap = cap_b;
@@ -1652,8 +1786,8 @@ static smb200_status ring_plan(smb200_crs* m, SpmvPlan& p, uint64_t rb, uint64_t
     // index compression: 16-bit window positions for the windowed blocks (the windows of one block hold <= xcap <= 65536
     // elements).  Costs 2 bytes per non-zero of plan memory and saves sizeof(I) - 2 of every column read.
     if (p.n_xwin > 0 && p.xcap <= 65536u && want_c16) {
-        p.lcols_base = ob & ~7ull;
-        const size_t n_l = (size_t)(oe - p.lcols_base) + 8;
+        p.lcols_base = ob & ~(kSliceAlign - 1);
+        const size_t n_l = (size_t)(oe - p.lcols_base) + kSliceAlign;
         SMB_CUDA(cudaMalloc(&p.lcols, n_l * sizeof(uint16_t) + kPadBytes));
         unsigned long long* d_n = nullptr;
         SMB_CUDA(cudaMalloc(&d_n, sizeof(unsigned long long)));
@@ -1833,7 +1967,10 @@ static smb200_status launch_typed(smb200_crs* m, const SpmvPlan& p, uint64_t rb,
             // without windows (borrowed, unpadded x) every block stages its full-width columns and no x
             const unsigned colb = (xwin_ok && p.colb == 2) ? 2u : (unsigned)sizeof(I);
             const unsigned xcap = xwin_ok ? p.xcap : 0u;
-            const size_t stage = (size_t)sh.cap * (sizeof(T) + colb) + (size_t)(p.ocap + 8) * (p.loffs ? 2 : sizeof(I)) + (size_t)xcap * sizeof(T);
+            // value indexing needs the packed layout (every block windowed) and one lane per row
+            const bool v8 = p.vcodes != nullptr && xwin_ok && colb == 2 && p.lanes <= 1;
+            const size_t stage = (size_t)sh.cap * ((v8 ? 1 : sizeof(T)) + colb) + (size_t)(p.ocap + 8) * (p.loffs ? 2 : sizeof(I)) +
+                                 (size_t)xcap * sizeof(T) + (v8 ? 256 * sizeof(T) : 0);
             // two CTAs per SM, two stages each: one block is consumed while the next one lands, and the second CTA's
             // consumers fill the issue slots the first one leaves idle
             int ctas = env_int("SMB200_RING_CTAS", 2);
@@ -1845,13 +1982,40 @@ static smb200_status launch_typed(smb200_crs* m, const SpmvPlan& p, uint64_t rb,
             while (stages > 2 && (stage * stages + 3072) * ctas > 227u * 1024u) --stages;
             if ((stage * stages + 3072) * ctas > 227u * 1024u) ctas = 1;
             const size_t smem = stage * stages;
-            SMB_REQUIRE(smem <= 224u * 1024u, SMB200_ERR_INVALID, "spmv: ring stage of %zu bytes does not fit shared memory", stage);
+            if (smem > 224u * 1024u) {
+                // A plan cut for compressed stages, launched without x windows (a borrowed, unpadded x): the full-width slices do
+                // not fit the ring.  Rare and not worth a second plan: one sub-warp per row straight from the CRS arrays.
+                const int l = pick_lanes(m->n_rows ? (double)m->nnz / (double)m->n_rows : 1.0);
+                const uint64_t rows = re - rb, rows_per_cta = (uint64_t)(kSpmvThreads / l);
+                const uint64_t grid = (rows + rows_per_cta - 1) / rows_per_cta;
+                SMB_REQUIRE(grid < 0x7FFFFFFFull, SMB200_ERR_UNSUPPORTED, "spmv: grid too large");
+                if constexpr (DOT) SMB_TRY(ensure_reduction_scratch(ctx, grid));
+                DotArgs d2 = dot;
+                if constexpr (DOT) { if (!g_redirect.partials) d2.partials = ctx->red_partials; }
+                switch (l) {
+#define SMB_VEC_CASE(L) case L: spmv_vector_kernel<T, I, L, DOT><<<(unsigned)grid, kSpmvThreads, 0, st>>>(vals, cols, offs, rb, re, xx, yy, d2); break;
+                    SMB_VEC_CASE(1) SMB_VEC_CASE(2) SMB_VEC_CASE(4) SMB_VEC_CASE(8) SMB_VEC_CASE(16) SMB_VEC_CASE(32)
+#undef SMB_VEC_CASE
+                }
+                g_last_pipe_grid = (unsigned)grid;
+                count_launch();
+                SMB_CUDA(cudaGetLastError());
+                if constexpr (DOT) {
+                    spmv_dot_finalize_kernel<<<1, kFinalizeThreads, 0, st>>>(d2.partials, g_last_pipe_grid, sizeof(T) == 4 ? 1 : 0, d2.result,
+                                                                           d2.roll_dst, d2.roll_src, d2.done);
+                    count_launch();
+                    SMB_CUDA(cudaGetLastError());
+                }
+                return SMB200_OK;
+            }
 
             const int rl = p.lanes > 1 ? p.lanes : 1;        // threads per row (plan: from the longest row)
-            auto kern = rl == 8 ? spmv_ring_kernel<T, I, DOT, false, 8> : rl == 4 ? spmv_ring_kernel<T, I, DOT, false, 4>
-                      : rl == 2 ? spmv_ring_kernel<T, I, DOT, false, 2> : spmv_ring_kernel<T, I, DOT, false, 1>;
-            auto kern_d = rl == 8 ? spmv_ring_kernel<T, I, DOT, true, 8> : rl == 4 ? spmv_ring_kernel<T, I, DOT, true, 4>
-                        : rl == 2 ? spmv_ring_kernel<T, I, DOT, true, 2> : spmv_ring_kernel<T, I, DOT, true, 1>;
+            auto kern = v8 ? spmv_ring_kernel<T, I, DOT, false, 1, true>
+                      : rl == 8 ? spmv_ring_kernel<T, I, DOT, false, 8, false> : rl == 4 ? spmv_ring_kernel<T, I, DOT, false, 4, false>
+                      : rl == 2 ? spmv_ring_kernel<T, I, DOT, false, 2, false> : spmv_ring_kernel<T, I, DOT, false, 1, false>;
+            auto kern_d = v8 ? spmv_ring_kernel<T, I, DOT, true, 1, true>
+                        : rl == 8 ? spmv_ring_kernel<T, I, DOT, true, 8, false> : rl == 4 ? spmv_ring_kernel<T, I, DOT, true, 4, false>
+                        : rl == 2 ? spmv_ring_kernel<T, I, DOT, true, 2, false> : spmv_ring_kernel<T, I, DOT, true, 1, false>;
             if (g_halo.host) SMB_CUDA(cudaFuncSetAttribute(kern_d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             else SMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             int resident = 0;
@@ -1870,12 +2034,13 @@ static smb200_status launch_typed(smb200_crs* m, const SpmvPlan& p, uint64_t rb,
                                                                  (unsigned)p.n_blocks, sh.cap, p.ocap, xcap, colb, (unsigned)stages, xwin_ok,
                                                                  xwin_ok ? p.lcols : nullptr, (unsigned long long)p.lcols_base, p.loffs,
                                                                  (unsigned long long)p.loffs_row_begin, xx, yy, dot, *g_halo.host,
-                                                                 (unsigned)(g_halo.rot % p.n_blocks));
+                                                                 (unsigned)(g_halo.rot % p.n_blocks), p.vcodes, (const T*)p.vdict);
             } else {
                 kern<<<(unsigned)grid, kRingThreads, smem, st>>>(vals, cols, offs, (const I*)p.blk_rows, (const I*)p.blk_nnz, p.seg_lo, p.seg_len,
                                                                (unsigned)p.n_blocks, sh.cap, p.ocap, xcap, colb, (unsigned)stages, xwin_ok,
                                                                xwin_ok ? p.lcols : nullptr, (unsigned long long)p.lcols_base, p.loffs,
-                                                               (unsigned long long)p.loffs_row_begin, xx, yy, dot, NoHalo(), 0u);
+                                                               (unsigned long long)p.loffs_row_begin, xx, yy, dot, NoHalo(), 0u, p.vcodes,
+                                                               (const T*)p.vdict);
             }
         } else if (p.variant == SMB200_SPMV_STREAM_PIPE) {
             int stages = env_int("SMB200_PIPE_STAGES", 3);
@@ -2071,6 +2236,8 @@ smb200_status smb200_crs_plan_info(const smb200_crs* cm, smb200_plan_info* out) 
     out->nnz_c16 = m->plan.n_c16;
     out->rows_o16 = m->plan.n_o16;
     out->stream_bytes = out->algorithmic_bytes - (m->plan.n_c16 + m->plan.n_o16) * (isize(m->it) - 2);
+    out->nnz_v8 = m->plan.n_v8;
+    if (m->plan.n_v8) out->stream_bytes = out->stream_bytes - m->plan.n_v8 * (vsize(m->vt) - 1) + m->plan.n_blocks * 256 * vsize(m->vt);
     if (m->plan.variant == SMB200_SPMV_BANDSPLIT) out->stream_bytes = bandsplit_stream_bytes(m, m->plan);
     out->plan_bytes = plan_device_bytes(m, m->plan);
     out->plan_ms = m->plan.build_ms;
