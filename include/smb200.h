@@ -121,6 +121,9 @@ typedef struct {
                                * distinct values (plan-time value indexing: every block holds <= 256 distinct values —
                                * constant-coefficient stencils, unit-weight graphs; same operands, bit-identical results);
                                * stream_bytes then counts 1 byte per value plus one 256-entry dictionary per block      */
+    uint64_t sell_entries;    /* RING, value-indexed: padded entries of the sliced-ELLPACK stage order (0: CRS order).  The
+                               * compressed entries of a block are stored 32 rows at a time, entry j of those rows side by
+                               * side, so a warp reads consecutive bytes; kept when the padding is below 20 %            */
 } smb200_plan_info;
 
 typedef struct {

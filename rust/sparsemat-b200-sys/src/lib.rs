@@ -60,6 +60,7 @@ pub struct smb200_plan_info {
     pub plan_bytes: u64,
     pub plan_ms: f64,
     pub nnz_v8: u64,
+    pub sell_entries: u64,
 }
 
 #[repr(C)]

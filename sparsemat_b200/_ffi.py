@@ -43,7 +43,7 @@ class PlanInfo(C.Structure):
                 ("n_rows", C.c_uint64), ("n_cols", C.c_uint64), ("nnz", C.c_uint64), ("max_row_len", C.c_uint64),
                 ("mean_row_len", C.c_double), ("algorithmic_bytes", C.c_uint64), ("launches_per_spmv", C.c_uint64),
                 ("n_xwin_blocks", C.c_uint64), ("nnz_c16", C.c_uint64), ("stream_bytes", C.c_uint64),
-                ("rows_o16", C.c_uint64), ("plan_bytes", C.c_uint64), ("plan_ms", C.c_double), ("nnz_v8", C.c_uint64)]
+                ("rows_o16", C.c_uint64), ("plan_bytes", C.c_uint64), ("plan_ms", C.c_double), ("nnz_v8", C.c_uint64), ("sell_entries", C.c_uint64)]
 
 
 class CgStats(C.Structure):

@@ -120,6 +120,15 @@ struct SpmvPlan {
     unsigned long long* seg_lo = nullptr; // RING: [4 * n_blocks] first column of each x segment of the block (aligned down)
     unsigned* seg_len = nullptr;        // RING: [4 * n_blocks] segment lengths in elements (0 = unused; all 0 = no window)
     unsigned ocap = 0, xcap = 0;        // RING: row-offset / x-window capacity of a stage (elements)
+    // RING, value-indexed plans in sliced-ELLPACK stage order (spmv_sell.cuh): the compressed entries of every block laid out
+    // 32 rows at a time the way a warp reads them; replaces vcodes / lcols / loffs when the padding is small
+    void* sell_blocks = nullptr;        //   [n_blocks] SellBlock
+    uint8_t* sell_codes = nullptr;      //   [sell_entries] value codes
+    uint16_t* sell_cols = nullptr;      //   [sell_entries] window positions
+    uint8_t* sell_rowlen = nullptr;     //   row lengths, each block padded to 16
+    uint32_t* sell_soff = nullptr;      //   slice offsets, n_slices + 1 per block, padded to 4
+    uint64_t sell_entries = 0, sell_rowbytes = 0, sell_soffwords = 0;
+    unsigned sell_ecap = 0, sell_rcap = 0, sell_scap = 0;
     uint8_t* vcodes = nullptr;          // RING, value indexing: 8-bit code of every non-zero into its block's dictionary
     void* vdict = nullptr;              //       [256 * n_blocks] dictionaries (T): the sorted distinct values of each block
     uint64_t n_v8 = 0;                  //       non-zeros whose value the kernel reads through a code

@@ -1171,6 +1171,10 @@ spmv_ring_kernel(const T* __restrict__ vals, const I* __restrict__ cols, const I
     if constexpr (DOT) finish_dot<T, kRingThreads>(acc, dot);
 }
 
+}  // namespace smb
+#include "spmv_sell.cuh"
+namespace smb {
+
 // Plan time, one CTA per block: find <= kNSeg windows of x that cover every column of the block.  Columns are
 // bucketed (2^shift columns per bucket) into a shared-memory bitmap, runs of set buckets (gaps of one bucket are
 // bridged) become windows, a second pass takes the exact [min, max] of each; blocks whose windows do not fit
@@ -1481,6 +1485,11 @@ void plan_free(SpmvPlan& p) {
     if (p.loffs) cudaFree(p.loffs);
     if (p.vcodes) cudaFree(p.vcodes);
     if (p.vdict) cudaFree(p.vdict);
+    if (p.sell_blocks) cudaFree(p.sell_blocks);
+    if (p.sell_codes) cudaFree(p.sell_codes);
+    if (p.sell_cols) cudaFree(p.sell_cols);
+    if (p.sell_rowlen) cudaFree(p.sell_rowlen);
+    if (p.sell_soff) cudaFree(p.sell_soff);
     if (p.blk_win) cudaFree(p.blk_win);
     for (smb200_crs* part : p.parts) smb200_crs_free(part);
     p = SpmvPlan();
@@ -1575,7 +1584,9 @@ static uint64_t plan_device_bytes(const smb200_crs* m, const SpmvPlan& p) {
     if (p.seg_len) b += (uint64_t)kNSeg * p.n_blocks * 4;
     if (p.lcols) b += (p.n_c16 ? p.n_c16 : m->nnz) * 2 + kPadBytes;
     if (p.loffs) b += (p.n_o16 + 8 * p.n_blocks + 16) * 2 + kPadBytes;
-    if (p.vcodes) b += p.n_v8 + kPadBytes + p.n_blocks * 256 * vsize(m->vt);
+    if (p.vcodes) b += p.n_v8 + kPadBytes;
+    if (p.vdict) b += p.n_blocks * 256 * vsize(m->vt);
+    if (p.sell_blocks) b += p.n_blocks * sizeof(SellBlock) + 3 * p.sell_entries + p.sell_rowbytes + 4 * p.sell_soffwords;
     if (p.blk_win) b += 2 * p.n_blocks * is;
     for (const smb200_crs* part : p.parts)
         b += part->nnz * (vsize(part->vt) + isize(part->it)) + (part->n_rows + 1) * isize(part->it) + plan_device_bytes(part, part->plan);
@@ -1678,6 +1689,80 @@ __global__ void block_extent_kernel(const I* __restrict__ blk_rows, const I* __r
 }
 
 constexpr size_t kRingStageBudget = 55 * 1024;   // two CTAs/SM x two stages (+ static shared memory) inside 227 KB
+
+// Value-indexed, packed ring plan -> sliced-ELLPACK stage order (spmv_sell.cuh).  Kept when the padding is below 20 % and the
+// stage still fits; p.vcodes / p.lcols / p.loffs (CRS order) are then released.
+template <class I>
+static smb200_status ring_sell_build(smb200_crs* m, SpmvPlan& p) {
+    smb200_ctx* ctx = m->ctx;
+    cudaStream_t st = ctx->stream;
+    const size_t ts = vsize(m->vt);
+    const uint64_t n = p.n_blocks;
+    std::vector<I> h_rows(n + 1);
+    SMB_CUDA(cudaMemcpyAsync(h_rows.data(), p.blk_rows, (n + 1) * sizeof(I), cudaMemcpyDeviceToHost, st));
+    SMB_CUDA(cudaStreamSynchronize(st));
+    std::vector<unsigned long long> slice_base(n + 1), rows_of(n);
+    unsigned long long total_slices = 0;
+    for (uint64_t b = 0; b < n; ++b) {
+        rows_of[b] = (unsigned long long)h_rows[b + 1] - (unsigned long long)h_rows[b];
+        if (rows_of[b] > 65536) return SMB200_OK;                      // (sell_fill_kernel's slice table)
+        slice_base[b] = total_slices;
+        total_slices += (rows_of[b] + 31) / 32;
+    }
+    slice_base[n] = total_slices;
+    unsigned long long *d_sb = nullptr, *d_rows = nullptr, *d_sz = nullptr;
+    unsigned* d_w = nullptr;
+    auto cleanup = [&] { if (d_sb) cudaFree(d_sb); if (d_rows) cudaFree(d_rows); if (d_sz) cudaFree(d_sz); if (d_w) cudaFree(d_w); };
+#define SELL_CUDA(expr) do { cudaError_t se__ = (expr); if (se__ != cudaSuccess) { cleanup(); SMB_CUDA(se__); } } while (0)
+    SELL_CUDA(cudaMalloc(&d_sb, (n + 1) * 8));
+    SELL_CUDA(cudaMalloc(&d_rows, n * 8));
+    SELL_CUDA(cudaMalloc(&d_sz, 3 * n * 8));
+    SELL_CUDA(cudaMalloc(&d_w, (total_slices + 1) * 4));
+    SELL_CUDA(cudaMemcpyAsync(d_sb, slice_base.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
+    SELL_CUDA(cudaMemcpyAsync(d_rows, rows_of.data(), n * 8, cudaMemcpyHostToDevice, st));
+    sell_width_kernel<I><<<(unsigned)n, 256, 0, st>>>((const I*)m->offsets, (const I*)p.blk_rows, d_sb, n, d_w);
+    sell_block_sizes_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d_w, d_sb, d_rows, n, d_sz, d_sz + n, d_sz + 2 * n);
+    count_launch(2);
+    std::vector<unsigned long long> sz(3 * n);
+    SELL_CUDA(cudaMemcpyAsync(sz.data(), d_sz, 3 * n * 8, cudaMemcpyDeviceToHost, st));
+    SELL_CUDA(cudaStreamSynchronize(st));
+    std::vector<unsigned long long> bases(3 * n);
+    unsigned long long E = 0, R = 0, S = 0, ecap = 0, rcap = 0, scap = 0;
+    for (uint64_t b = 0; b < n; ++b) {
+        bases[b] = E; bases[n + b] = R; bases[2 * n + b] = S;
+        E += sz[b]; R += sz[n + b]; S += sz[2 * n + b];
+        ecap = std::max(ecap, sz[b]); rcap = std::max(rcap, sz[n + b]); scap = std::max(scap, sz[2 * n + b]);
+    }
+    const size_t stage = 3 * (size_t)ecap + (size_t)rcap + 4 * (size_t)scap + (size_t)p.xcap * ts + 256 * ts;
+    const bool keep = (double)E <= 1.2 * (double)p.n_v8 + 4096.0 && (stage * 2 + 3072) * 2 <= 227u * 1024u && ecap < (1ull << 31);
+    if (!keep) { cleanup(); return SMB200_OK; }
+    SELL_CUDA(cudaMemcpyAsync(d_sz, bases.data(), 3 * n * 8, cudaMemcpyHostToDevice, st));
+    SELL_CUDA(cudaMalloc(&p.sell_blocks, n * sizeof(SellBlock)));
+    SELL_CUDA(cudaMalloc(&p.sell_codes, E + kPadBytes));
+    SELL_CUDA(cudaMalloc(&p.sell_cols, 2 * E + kPadBytes));
+    SELL_CUDA(cudaMalloc(&p.sell_rowlen, R + kPadBytes));
+    SELL_CUDA(cudaMalloc(&p.sell_soff, 4 * S + kPadBytes));
+    cudaMemsetAsync(p.sell_codes, 0, E + kPadBytes, st);
+    cudaMemsetAsync(p.sell_cols, 0, 2 * E + kPadBytes, st);
+    cudaMemsetAsync(p.sell_rowlen, 0, R + kPadBytes, st);
+    cudaMemsetAsync(p.sell_soff, 0, 4 * S + kPadBytes, st);
+    const unsigned long long g0 = m->x_extra ? ((m->n_rows + 63) & ~(uint64_t)63) : ~0ull;     // dist.cu: ghosts from n_rows rounded up to 64
+    sell_fill_kernel<I><<<(unsigned)n, 256, 0, st>>>((const I*)m->offsets, (const I*)p.blk_rows, d_w, d_sb, d_sz, d_sz + n, d_sz + 2 * n,
+                                                    p.vcodes, p.lcols, p.lcols_base, p.seg_lo, p.seg_len, g0, p.sell_codes, p.sell_cols,
+                                                    p.sell_rowlen, p.sell_soff, (SellBlock*)p.sell_blocks);
+    count_launch();
+    SELL_CUDA(cudaGetLastError());
+    SELL_CUDA(cudaStreamSynchronize(st));
+#undef SELL_CUDA
+    cleanup();
+    p.sell_entries = E; p.sell_rowbytes = R; p.sell_soffwords = S;
+    p.sell_ecap = (unsigned)ecap; p.sell_rcap = (unsigned)rcap; p.sell_scap = (unsigned)scap;
+    // the CRS-order compressed arrays are not read any more
+    cudaFree(p.vcodes); p.vcodes = nullptr;
+    cudaFree(p.lcols); p.lcols = nullptr;
+    if (p.loffs) { cudaFree(p.loffs); p.loffs = nullptr; p.n_o16 = 0; }      // (a length byte per row instead)
+    return SMB200_OK;
+}
 
 // RING plan.  A stage holds [values cap*T][columns cap*colb][row offsets (ocap+8)*I][x windows xcap*T].
 //  (a) packed: every block windowed, columns staged as 16-bit window positions (colb = 2), capacities taken from the
@@ -1814,6 +1899,10 @@ static smb200_status ring_plan(smb200_crs* m, SpmvPlan& p, uint64_t rb, uint64_t
         SMB_CUDA(cudaGetLastError());
         p.loffs_row_begin = rb;
         p.n_o16 = rows;
+    }
+    if (v8 && p.lcols && p.n_c16 == nnz && env_int("SMB200_RING_SELL", 1) != 0) {
+        if (m->it == SMB200_U64) SMB_TRY(ring_sell_build<uint64_t>(m, p));
+        else SMB_TRY(ring_sell_build<uint32_t>(m, p));
     }
     return SMB200_OK;
 }
@@ -1967,6 +2056,36 @@ static smb200_status launch_typed(smb200_crs* m, const SpmvPlan& p, uint64_t rb,
             // without windows (borrowed, unpadded x) every block stages its full-width columns and no x
             const unsigned colb = (xwin_ok && p.colb == 2) ? 2u : (unsigned)sizeof(I);
             const unsigned xcap = xwin_ok ? p.xcap : 0u;
+            if (p.sell_blocks && xwin_ok) {
+                // value-indexed plan in sliced-ELLPACK stage order (spmv_sell.cuh)
+                const size_t stage = 3 * (size_t)p.sell_ecap + (size_t)p.sell_rcap + 4 * (size_t)p.sell_scap + (size_t)xcap * sizeof(T) + 256 * sizeof(T);
+                int stages = env_int("SMB200_RING_STAGES", 2);
+                if (stages < 2) stages = 2;
+                if (stages > kPipeMaxStages) stages = kPipeMaxStages;
+                while (stages > 2 && (stage * stages + 3072) * 2 > 227u * 1024u) --stages;
+                const size_t smem = stage * stages;
+                auto kern = spmv_ring_sell_kernel<T, DOT, false>;
+                auto kern_d = spmv_ring_sell_kernel<T, DOT, true>;
+                if (g_halo.host) SMB_CUDA(cudaFuncSetAttribute(kern_d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                else SMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                int resident = 0;
+                if (g_halo.host) SMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern_d, kRingThreads, smem));
+                else SMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, kRingThreads, smem));
+                if (resident < 1) resident = 1;
+                if (resident > 2) resident = 2;
+                uint64_t grid = (uint64_t)ctx->sm_count * (uint64_t)resident;
+                if (grid > p.n_blocks) grid = p.n_blocks;
+                if (g_ring_grid_cap > 0 && grid > (uint64_t)g_ring_grid_cap) grid = (uint64_t)g_ring_grid_cap;
+                g_last_pipe_grid = (unsigned)grid;
+                if (g_halo.host)
+                    kern_d<<<(unsigned)grid, kRingThreads, smem, st>>>((const SellBlock*)p.sell_blocks, p.sell_codes, p.sell_cols, p.sell_rowlen, p.sell_soff,
+                                                                     (const T*)p.vdict, (unsigned)p.n_blocks, p.sell_ecap, p.sell_rcap, p.sell_scap, xcap,
+                                                                     (unsigned)stages, xx, yy, dot, *g_halo.host, (unsigned)(g_halo.rot % p.n_blocks));
+                else
+                    kern<<<(unsigned)grid, kRingThreads, smem, st>>>((const SellBlock*)p.sell_blocks, p.sell_codes, p.sell_cols, p.sell_rowlen, p.sell_soff,
+                                                                   (const T*)p.vdict, (unsigned)p.n_blocks, p.sell_ecap, p.sell_rcap, p.sell_scap, xcap,
+                                                                   (unsigned)stages, xx, yy, dot, NoHalo(), 0u);
+            } else {
             // value indexing needs the packed layout (every block windowed) and one lane per row
             const bool v8 = p.vcodes != nullptr && xwin_ok && colb == 2 && p.lanes <= 1;
             const size_t stage = (size_t)sh.cap * ((v8 ? 1 : sizeof(T)) + colb) + (size_t)(p.ocap + 8) * (p.loffs ? 2 : sizeof(I)) +
@@ -1984,8 +2103,9 @@ static smb200_status launch_typed(smb200_crs* m, const SpmvPlan& p, uint64_t rb,
             const size_t smem = stage * stages;
             if (smem > 224u * 1024u) {
                 // A plan cut for compressed stages, launched without x windows (a borrowed, unpadded x): the full-width slices do
-                // not fit the ring.  Rare and not worth a second plan: one sub-warp per row straight from the CRS arrays.
-                const int l = pick_lanes(m->n_rows ? (double)m->nnz / (double)m->n_rows : 1.0);
+                // not fit the ring.  Rare and not worth a second plan: straight from the CRS arrays, one thread per row where the
+                // plan sums rows in storage order (so the result stays bit-identical), a sub-warp per row otherwise.
+                const int l = p.lanes <= 1 ? 1 : pick_lanes(m->n_rows ? (double)m->nnz / (double)m->n_rows : 1.0);
                 const uint64_t rows = re - rb, rows_per_cta = (uint64_t)(kSpmvThreads / l);
                 const uint64_t grid = (rows + rows_per_cta - 1) / rows_per_cta;
                 SMB_REQUIRE(grid < 0x7FFFFFFFull, SMB200_ERR_UNSUPPORTED, "spmv: grid too large");
@@ -2041,6 +2161,7 @@ static smb200_status launch_typed(smb200_crs* m, const SpmvPlan& p, uint64_t rb,
                                                                xwin_ok ? p.lcols : nullptr, (unsigned long long)p.lcols_base, p.loffs,
                                                                (unsigned long long)p.loffs_row_begin, xx, yy, dot, NoHalo(), 0u, p.vcodes,
                                                                (const T*)p.vdict);
+            }
             }
         } else if (p.variant == SMB200_SPMV_STREAM_PIPE) {
             int stages = env_int("SMB200_PIPE_STAGES", 3);
@@ -2238,6 +2359,10 @@ smb200_status smb200_crs_plan_info(const smb200_crs* cm, smb200_plan_info* out) 
     out->stream_bytes = out->algorithmic_bytes - (m->plan.n_c16 + m->plan.n_o16) * (isize(m->it) - 2);
     out->nnz_v8 = m->plan.n_v8;
     if (m->plan.n_v8) out->stream_bytes = out->stream_bytes - m->plan.n_v8 * (vsize(m->vt) - 1) + m->plan.n_blocks * 256 * vsize(m->vt);
+    if (m->plan.sell_blocks)        // padded 3-byte entries, a length byte per row, an offset word per slice, the dictionaries, x and y
+        out->stream_bytes = 3 * m->plan.sell_entries + m->plan.sell_rowbytes + 4 * m->plan.sell_soffwords + m->plan.n_blocks * (256 * vsize(m->vt) + sizeof(SellBlock)) +
+                            (m->n_cols + m->n_rows) * vsize(m->vt);
+    out->sell_entries = m->plan.sell_entries;
     if (m->plan.variant == SMB200_SPMV_BANDSPLIT) out->stream_bytes = bandsplit_stream_bytes(m, m->plan);
     out->plan_bytes = plan_device_bytes(m, m->plan);
     out->plan_ms = m->plan.build_ms;

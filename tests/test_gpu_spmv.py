@@ -4,6 +4,8 @@ sparsemat_crs.rs:102-110) — libsmb200's SpMV kernels against the oracle on ide
 Bar (BASELINE.json north_star): bit-exact wherever a row is summed in storage order (scalar kernel; the
 stream kernels for rows of <= 64 entries), otherwise |got - want| <= tol * (|A||x|)_i with tol = 1e-5 (f32) /
 1e-12 (f64)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -131,10 +133,32 @@ def test_ring_kernel_windows_and_fallbacks(smb, orc, ctx, vdt, idt):
         a = smb.SparseMatCRS.from_raw_parts(ctx, n, n, vals, cols, offs).configure(smb.SPMV_RING)
         info = a.plan_info()
         assert info["variant"] == smb.SPMV_RING and info["n_xwin_blocks"] == info["n_blocks"]   # every block got its windows
-        # ... and with them 16-bit window positions instead of its columns (plan-time index compression)
-        # and, the plan being packed, 16-bit block-relative row offsets as well
-        assert info["nnz_c16"] == vals.size and info["rows_o16"] == n
-        assert info["stream_bytes"] == info["algorithmic_bytes"] - (vals.size + n) * (np.dtype(idt).itemsize - 2)
+        # ... and with them 16-bit window positions instead of its columns (plan-time index compression); the Laplacian has
+        # two distinct values, so every block also gets a dictionary and 8-bit value codes (value indexing), and the padding
+        # of the sliced-ELLPACK stage order is small
+        assert info["nnz_c16"] == vals.size and info["nnz_v8"] == vals.size
+        assert vals.size <= info["sell_entries"] <= 1.2 * vals.size + 4096
+        assert info["stream_bytes"] < info["algorithmic_bytes"] - vals.size * (np.dtype(idt).itemsize - 2)
+        # without value indexing: the packed CRS-order stage with 16-bit block-relative row offsets
+        os.environ["SMB200_RING_V8"] = "0"
+        try:
+            a.configure(smb.SPMV_RING)
+            info = a.plan_info()
+            assert info["nnz_c16"] == vals.size and info["rows_o16"] == n and info["nnz_v8"] == 0 and info["sell_entries"] == 0
+            assert info["stream_bytes"] == info["algorithmic_bytes"] - (vals.size + n) * (np.dtype(idt).itemsize - 2)
+            x0 = orc.uniform(vdt, 21, n)
+            assert np.array_equal(a.mvp(smb.DenseVec.from_vec(ctx, x0)).to_numpy(), orc.mvp(vals, cols, offs, x0))
+            # value indexing in CRS stage order (no sliced-ELLPACK)
+            os.environ["SMB200_RING_V8"] = "1"
+            os.environ["SMB200_RING_SELL"] = "0"
+            a.configure(smb.SPMV_RING)
+            info = a.plan_info()
+            assert info["nnz_v8"] == vals.size and info["sell_entries"] == 0 and info["rows_o16"] == n
+            assert np.array_equal(a.mvp(smb.DenseVec.from_vec(ctx, x0)).to_numpy(), orc.mvp(vals, cols, offs, x0))
+        finally:
+            os.environ.pop("SMB200_RING_V8", None)
+            os.environ.pop("SMB200_RING_SELL", None)
+        a.configure(smb.SPMV_RING)
         x = orc.uniform(vdt, 21, n)
         want = orc.mvp(vals, cols, offs, x)
         xd = smb.DenseVec.from_vec(ctx, x)
@@ -414,3 +438,38 @@ def test_ring_kernel_long_rows_multi_lane(smb, orc, ctx, vdt, idt):
             bil = float(a.inner_prod(smb.DenseVec.from_vec(ctx, lhs), xd))
             ref = float(np.sum(lhs.astype(np.float64) * want.astype(np.float64)))
             assert abs(bil - ref) <= 1e-5 * float(np.sum(np.abs(lhs.astype(np.float64)) * scale)) + 1e-30
+
+
+def test_value_indexing_is_exact_and_optional(smb, orc, ctx):
+    """Plan-time value indexing (8-bit codes into per-block dictionaries of <= 256 distinct values): taken for matrices with few
+    distinct values, left alone otherwise; results bit-identical either way; scale() reaches the dictionaries; special values
+    (-0.0, inf, nan payloads) survive the dictionary."""
+    n = 20
+    vals, cols, offs = orc.laplace(F64, U32, n, n, n)
+    N = n ** 3
+    x = orc.uniform(F64, 5, N)
+    a = smb.SparseMatCRS.from_raw_parts(ctx, N, N, vals, cols, offs)
+    assert a.plan_info()["nnz_v8"] == vals.size
+    xd = smb.DenseVec.from_vec(ctx, x)
+    assert np.array_equal(a.mvp(xd).to_numpy(), orc.mvp(vals, cols, offs, x))
+    a.scale(0.37)                                                            # sparsemat_crs.rs:153-157: every later product sees it
+    assert np.array_equal(a.mvp(xd).to_numpy(), orc.mvp(vals * 0.37, cols, offs, x))
+    # a handful of special values in an otherwise two-valued matrix
+    v2 = vals.copy()
+    v2[5], v2[77], v2[1234], v2[4000] = -0.0, np.inf, np.nan, 5e-324
+    b = smb.SparseMatCRS.from_raw_parts(ctx, N, N, v2, cols, offs)
+    assert b.plan_info()["nnz_v8"] == vals.size
+    got, want = b.mvp(xd).to_numpy(), orc.mvp(v2, cols, offs, x)
+    assert got.tobytes() == want.tobytes()                                   # NaN rows included: the same bits
+    # random values: more than 256 distinct ones per block -> the plan keeps full-width values
+    v3 = np.random.default_rng(3).uniform(-1, 1, vals.size)
+    c = smb.SparseMatCRS.from_raw_parts(ctx, N, N, v3, cols, offs)
+    info = c.plan_info()
+    assert info["variant"] == smb.SPMV_RING and info["nnz_v8"] == 0 and info["sell_entries"] == 0 and info["nnz_c16"] == vals.size
+    assert np.array_equal(c.mvp(xd).to_numpy(), orc.mvp(v3, cols, offs, x))
+    # 300 distinct values in ONE block only: still no value indexing anywhere (the stage format is per plan)
+    v4 = vals.copy()
+    v4[:300] = np.arange(300) * 0.5 + 7.0
+    d = smb.SparseMatCRS.from_raw_parts(ctx, N, N, v4, cols, offs)
+    assert d.plan_info()["nnz_v8"] == 0
+    assert np.array_equal(d.mvp(xd).to_numpy(), orc.mvp(v4, cols, offs, x))
