@@ -488,16 +488,21 @@ def run_ours(args):
     kernel_ms = ms_per_step
     phys = int(plan["stream_bytes"])
     roof = {"bound": "hbm", "achieved": B_local / (kernel_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-            # frac: bytes the kernel physically streams (plan-time 16-bit window positions and row offsets instead of the
-            # u32 columns / offsets; ncu DRAM traffic agrees to 0.3 %) / time / peak.  frac_effective: the ALGORITHMIC bytes
-            # of the CRS format / time / peak — above 1 because the kernel moves fewer bytes than the format holds.
+            # frac: bytes the kernel physically streams (plan-time compression: 16-bit window positions instead of columns,
+            # 8-bit value codes + per-block dictionaries instead of values, a length byte per row instead of an offset; ncu DRAM
+            # traffic: `traffic`) / time / peak.  frac_effective: the ALGORITHMIC bytes of the CRS format / time /
+            # peak — above 1 because the kernel moves fewer bytes than the format holds.
             "frac": phys / (kernel_ms * 1e-3) / 1e9 / peak, "frac_effective": B_local / (kernel_ms * 1e-3) / 1e9 / peak,
             "achieved_physical": phys / (kernel_ms * 1e-3) / 1e9,
             "traffic": ncu_traffic(), "peak_source": peak_src,
             "frac_of_nominal_8tbs": phys / (kernel_ms * 1e-3) / 1e9 / 8000.0,
-            "kernel": f"spmv_{plan['variant_name']}" + (" (one launch per product incl. the in-kernel halo push / wait)" if multi else ""),
+            "kernel": f"spmv_{plan['variant_name']}" + ("_sell" if plan["sell_entries"] else "") +
+                      (" (one launch per product incl. the in-kernel halo push / wait)" if multi else ""),
             "algorithmic_bytes_per_launch": B_local, "physical_bytes_per_launch": phys, "kernel_ms": kernel_ms,
             "nnz_with_16bit_columns": int(plan["nnz_c16"]), "rows_with_16bit_offsets": int(plan["rows_o16"]),
+            # plan-time value indexing (8-bit codes into per-block dictionaries of <= 256 distinct values; the 7-point Laplacian
+            # has two) and the sliced-ELLPACK stage order of the compressed entries (padded entries counted in physical bytes)
+            "nnz_with_8bit_value_codes": int(plan["nnz_v8"]), "sell_padded_entries": int(plan["sell_entries"]),
             # the plan is built once per matrix, outside the timed region: its cost, stated
             "plan_ms": plan["plan_ms"], "plan_extra_bytes": int(plan["plan_bytes"]),
             "plan_extra_frac_of_crs": plan["plan_bytes"] / float(B_local)}
