@@ -1,6 +1,8 @@
 #!/usr/bin/env python
-"""GPU, under compute-sanitizer: every kernel family on small matrices of all four type combinations, the vector
-kernels, CG, to_crs and the host pipeline.  Small on purpose (the sanitizer slows kernels down ~50x)."""
+"""GPU: every kernel family on small matrices of all four type combinations, the vector kernels, CG, to_crs and the host
+pipeline, each checked against the oracle — small on purpose so that the same command can be run under
+`compute-sanitizer --tool memcheck` where that tool is available (it is closed on this pool's boxes: gpurun answers that the
+tool is unavailable, so here the script only runs plain, from tests/test_gpu_spmv.py)."""
 import os
 import sys
 

@@ -15,6 +15,7 @@
 // stop test fires the remaining kernels of a batch exit immediately, leaving x, r, p untouched — the
 // reference's `break` (linearsolver.rs:52-54).
 #include "common.cuh"
+#include "halo.cuh"
 #include "reduce.cuh"
 
 #include <cmath>
@@ -106,8 +107,9 @@ template <class T, bool PRE>
 __global__ void __launch_bounds__(kCgThreads)
 cg_update_xr_kernel(T* __restrict__ x, T* __restrict__ r, const T* __restrict__ p, const T* __restrict__ ap, uint64_t n,
                     double* __restrict__ S, int rr_slot, double* __restrict__ partials, unsigned int* __restrict__ ticket, int vec_ok,
-                    const T* __restrict__ dinv) {
+                    const T* __restrict__ dinv, const ArDev* __restrict__ ar) {
     __shared__ double scratch[kCgThreads / 32 + 1];
+    __shared__ double ar_sv[kMaxPeers][kArSlots], ar_in[kArSlots], ar_out[kArSlots];
     if (__ldcg(S + S_DONE) != 0.0) return;
     const T alpha = div_rn((T)__ldcg(S + S_RR), (T)(__ldcg(S + S_PAP) + __ldcg(S + S_PAP + 1) + __ldcg(S + S_PAP + 2)));
     using V = typename Vec16<T>::type;
@@ -153,8 +155,19 @@ cg_update_xr_kernel(T* __restrict__ x, T* __restrict__ r, const T* __restrict__ 
     } else {
         const double bsum = block_sum<kCgThreads>(acc, scratch);
         double total;
-        if (grid_sum<kCgThreads>(bsum, partials, ticket, scratch, total))
-            if (threadIdx.x == 0) S[rr_slot] = (double)(T)total;
+        if (grid_sum<kCgThreads>(bsum, partials, ticket, scratch, total)) {
+            if (ar != nullptr) {
+                // one rank per GPU: the CTA that finished last exchanges the ranks' r.r through peer memory (halo.cuh) and
+                // leaves the global value, rounded to T like the reference's scalar, where the p update expects it
+                if (threadIdx.x == 0) ar_in[0] = total;
+                __syncthreads();
+                if (threadIdx.x < 32) ar_warp_allreduce(*ar, ar_in, ar_out, 1, ar_sv);
+                __syncthreads();
+                if (threadIdx.x == 0) S[S_RR_NEW] = (double)(T)ar_out[0];
+            } else if (threadIdx.x == 0) {
+                S[rr_slot] = (double)(T)total;
+            }
+        }
     }
 }
 
@@ -247,15 +260,15 @@ smb200_status cg_init_launch(smb200_ctx* ctx, CgWork& w, int vt, const void* b, 
     return SMB200_OK;
 }
 
-smb200_status cg_xr_launch(smb200_ctx* ctx, CgWork& w, int vt, void* x, uint64_t n, const void* dinv) {
+smb200_status cg_xr_launch(smb200_ctx* ctx, CgWork& w, int vt, void* x, uint64_t n, const void* dinv, const ArDev* ar) {
     const unsigned g = cg_grid(ctx, n, vt);
     const int slot = ctx->world > 1 ? S_RR_LOCAL : S_RR_NEW;
     const int vec_ok = ((uintptr_t)x & 15u) == 0 ? 1 : 0;
     if (dinv) {
-        if (vt == SMB200_F64) cg_update_xr_kernel<double, true><<<g, kCgThreads, 0, ctx->stream>>>((double*)x, (double*)w.r, (const double*)w.p, (const double*)w.ap, n, w.scalars, slot, ctx->red_partials, ctx->red_ticket, vec_ok, (const double*)dinv);
-        else cg_update_xr_kernel<float, true><<<g, kCgThreads, 0, ctx->stream>>>((float*)x, (float*)w.r, (const float*)w.p, (const float*)w.ap, n, w.scalars, slot, ctx->red_partials, ctx->red_ticket, vec_ok, (const float*)dinv);
-    } else if (vt == SMB200_F64) cg_update_xr_kernel<double, false><<<g, kCgThreads, 0, ctx->stream>>>((double*)x, (double*)w.r, (const double*)w.p, (const double*)w.ap, n, w.scalars, slot, ctx->red_partials, ctx->red_ticket, vec_ok, nullptr);
-    else cg_update_xr_kernel<float, false><<<g, kCgThreads, 0, ctx->stream>>>((float*)x, (float*)w.r, (const float*)w.p, (const float*)w.ap, n, w.scalars, slot, ctx->red_partials, ctx->red_ticket, vec_ok, nullptr);
+        if (vt == SMB200_F64) cg_update_xr_kernel<double, true><<<g, kCgThreads, 0, ctx->stream>>>((double*)x, (double*)w.r, (const double*)w.p, (const double*)w.ap, n, w.scalars, slot, ctx->red_partials, ctx->red_ticket, vec_ok, (const double*)dinv, nullptr);
+        else cg_update_xr_kernel<float, true><<<g, kCgThreads, 0, ctx->stream>>>((float*)x, (float*)w.r, (const float*)w.p, (const float*)w.ap, n, w.scalars, slot, ctx->red_partials, ctx->red_ticket, vec_ok, (const float*)dinv, nullptr);
+    } else if (vt == SMB200_F64) cg_update_xr_kernel<double, false><<<g, kCgThreads, 0, ctx->stream>>>((double*)x, (double*)w.r, (const double*)w.p, (const double*)w.ap, n, w.scalars, slot, ctx->red_partials, ctx->red_ticket, vec_ok, nullptr, ar);
+    else cg_update_xr_kernel<float, false><<<g, kCgThreads, 0, ctx->stream>>>((float*)x, (float*)w.r, (const float*)w.p, (const float*)w.ap, n, w.scalars, slot, ctx->red_partials, ctx->red_ticket, vec_ok, nullptr, ar);
     count_launch();
     SMB_CUDA(cudaGetLastError());
     return SMB200_OK;
@@ -309,9 +322,16 @@ smb200_status cg_solve_impl(smb200_crs* a, const smb200_vec* b, smb200_vec* x, d
         SMB_TRY(fetch_result(ctx, 0, &bb));
         threshold = tol * sqrt(bb);
     }
-    cudaEvent_t ev0, ev1;
-    SMB_CUDA(cudaEventCreate(&ev0));
-    SMB_CUDA(cudaEventCreate(&ev1));
+    struct Events {                       // destroyed on every return path
+        cudaEvent_t ev0 = nullptr, ev1 = nullptr, poll[2] = {nullptr, nullptr};
+        ~Events() { for (cudaEvent_t e : {ev0, ev1, poll[0], poll[1]}) if (e) cudaEventDestroy(e); }
+    } evs;
+    SMB_CUDA(cudaEventCreate(&evs.ev0));
+    SMB_CUDA(cudaEventCreate(&evs.ev1));
+    SMB_CUDA(cudaEventCreateWithFlags(&evs.poll[0], cudaEventDisableTiming));
+    SMB_CUDA(cudaEventCreateWithFlags(&evs.poll[1], cudaEventDisableTiming));
+    cudaEvent_t ev0 = evs.ev0, ev1 = evs.ev1;
+    cudaEvent_t* poll_ev = evs.poll;
     SMB_CUDA(cudaEventRecord(ev0, ctx->stream));
 
     double init[S_COUNT] = {0};
@@ -332,9 +352,6 @@ smb200_status cg_solve_impl(smb200_crs* a, const smb200_vec* b, smb200_vec* x, d
     if (batch < 1) batch = 1;
 
     uint64_t launched = 0;
-    cudaEvent_t poll_ev[2];
-    SMB_CUDA(cudaEventCreateWithFlags(&poll_ev[0], cudaEventDisableTiming));
-    SMB_CUDA(cudaEventCreateWithFlags(&poll_ev[1], cudaEventDisableTiming));
     smb200_status st = SMB200_OK;
     uint64_t rounds = 0;
     bool finished = false;
@@ -409,8 +426,6 @@ smb200_status cg_solve_impl(smb200_crs* a, const smb200_vec* b, smb200_vec* x, d
     } else {
         cudaStreamSynchronize(ctx->stream);
     }
-    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
-    cudaEventDestroy(poll_ev[0]); cudaEventDestroy(poll_ev[1]);
     return st;
 }
 

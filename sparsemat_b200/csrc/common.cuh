@@ -221,6 +221,10 @@ extern thread_local bool g_spmv_band;
 // Set by dist.cu around the ONE ring launch of a distributed product: the kernel then also runs the halo protocol of
 // halo.cuh (push the neighbours' ghost entries, wait for this rank's) and walks the row blocks rotated by `rot`.
 struct HaloDev;
+struct ArDev;
+// Set by dist.cu around the product of a distributed CG iteration: the fused dot's finalize kernel then all-reduces the
+// ranks' totals through peer memory (halo.cuh) instead of leaving that to a kernel of its own.
+extern thread_local const ArDev* g_dot_ar;
 struct HaloLaunch { const HaloDev* host = nullptr; uint64_t rot = 0; };     // host copy: passed to the kernel by value
 extern thread_local HaloLaunch g_halo;
 // Set while an SpMV reads a caller-owned (smb200_vec_wrap) vector: such memory has no padding behind its last element,
@@ -253,7 +257,7 @@ smb200_status gen_laplace_block(smb200_ctx* ctx, int vt, int it, uint64_t nx, ui
                                 smb200_crs** out, uint64_t ghost_base = 0);   // ghost_base 0: ghosts right behind the owned columns
 smb200_status cg_prepare(smb200_ctx* ctx, CgWork& w, int vt, uint64_t n, uint64_t p_cap, uint64_t iter_max);
 smb200_status cg_init_launch(smb200_ctx* ctx, CgWork& w, int vt, const void* b, uint64_t n, const void* dinv = nullptr);
-smb200_status cg_xr_launch(smb200_ctx* ctx, CgWork& w, int vt, void* x, uint64_t n, const void* dinv = nullptr);
+smb200_status cg_xr_launch(smb200_ctx* ctx, CgWork& w, int vt, void* x, uint64_t n, const void* dinv = nullptr, const ArDev* ar = nullptr);
 smb200_status cg_p_launch(smb200_ctx* ctx, CgWork& w, int vt, uint64_t n, const void* dinv = nullptr);
 smb200_status cg_solve_impl(smb200_crs* a, const smb200_vec* b, smb200_vec* x, double tol, int32_t relative,
                             uint64_t iter_max, smb200_cg_stats* stats, const void* dinv);

@@ -12,6 +12,7 @@ thread_local bool g_spmv_accumulate = false;
 thread_local bool g_spmv_band = false;
 thread_local bool g_x_unpadded = false;
 thread_local HaloLaunch g_halo;
+thread_local const ArDev* g_dot_ar = nullptr;
 
 void set_error(const char* fmt, ...) {
     va_list ap;

@@ -137,32 +137,11 @@ __global__ void __launch_bounds__(256) halo_wait_kernel(const HaloDev* __restric
 __global__ void __launch_bounds__(32) p2p_allreduce_kernel(const ArDev* __restrict__ a, const double* in, double* out, int count,
                                                            int round_f32) {
     __shared__ double sv[kMaxPeers][kArSlots];
-    const unsigned long long e = __ldcg(a->epoch) + 1ull;
-    const int world = a->world, me = a->me, q = (int)threadIdx.x;
-    const size_t par = (size_t)(e & 1ull);
-    if (q < world) {
-        double* dst = a->peer_vals[q] + (par * world + me) * kArSlots;
-        for (int k = 0; k < count; ++k) dst[k] = in[k];
-        __threadfence_system();
-        st_release_sys(a->peer_flags[q] + par * world + me, e);
-        const unsigned long long* f = a->flags + par * world + q;
-        const unsigned long long t0 = global_timer_ns();
-        unsigned spins = 0;
-        while (ld_acquire_sys(f) < e) {
-            if ((++spins & 255u) == 0 && global_timer_ns() - t0 > a->timeout_ns) { atomicExch(a->error, 1u); break; }
-        }
-        const double* src = a->vals + (par * world + q) * kArSlots;
-        for (int k = 0; k < count; ++k) sv[q][k] = __ldcg(src + k);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int k = 0; k < count; ++k) {
-            double sum = 0.0;
-            for (int r = 0; r < world; ++r) sum += sv[r][k];
-            out[k] = round_f32 ? (double)(float)sum : sum;
-        }
-        *a->epoch = e;
-    }
+    __shared__ double mine[kArSlots], res[kArSlots];
+    if (threadIdx.x < (unsigned)count) mine[threadIdx.x] = in[threadIdx.x];
+    __syncwarp();
+    ar_warp_allreduce(*a, mine, res, count, sv);
+    if (threadIdx.x < (unsigned)count) out[threadIdx.x] = round_f32 ? (double)(float)res[threadIdx.x] : res[threadIdx.x];
 }
 
 }  // namespace smb
@@ -953,12 +932,19 @@ smb200_status smb200_dist_cg_solve(smb200_dist* d, const smb200_vec* b, smb200_v
     // One iteration: halo exchange + SpMV with p.Ap fused (three launches) | all-reduce | x, r update + r.r | all-reduce | p update.
     // Every rank runs the same sequence: the stop flag derives from all-reduced values, hence is identical everywhere, and
     // iterations past it exit early on the device.
+    // With the ring kernel as the local product (ONE launch, one p.Ap slot) the two all-reduces ride inside the kernels that
+    // produce their operands — the fused dot's finalize kernel and the last CTA of the x / r update — so a distributed
+    // iteration is the same four launches as a single-GPU one.  Other local plans keep the two 1-CTA all-reduce kernels.
+    const bool fused_ar = multi && d->p2p && dist_exchanges(d) && a->plan.built && a->plan.variant == SMB200_SPMV_RING;
     auto iteration = [&]() -> smb200_status {
-        if (multi && cudaMemsetAsync(S + S_PAP, 0, 3 * sizeof(double), ctx->stream) != cudaSuccess) { set_error("dist_cg_solve: memset failed"); return SMB200_ERR_CUDA; }
-        SMB_TRY(dist_spmv_impl(d, w.p, w.ap, S));
-        if (multi) SMB_TRY(dist_allreduce(d, S + S_PAP, S + S_PAP, 3, false));
-        SMB_TRY(cg_xr_launch(ctx, w, d->vt, x->d, n));
-        if (multi) SMB_TRY(dist_allreduce(d, S + S_RR_LOCAL, S + S_RR_NEW, 1, f32));     // r.r is a T in the reference: rounded like the single-GPU path
+        if (multi && !fused_ar && cudaMemsetAsync(S + S_PAP, 0, 3 * sizeof(double), ctx->stream) != cudaSuccess) { set_error("dist_cg_solve: memset failed"); return SMB200_ERR_CUDA; }
+        g_dot_ar = fused_ar ? d->ar_dev : nullptr;
+        const smb200_status sp = dist_spmv_impl(d, w.p, w.ap, S);
+        g_dot_ar = nullptr;
+        SMB_TRY(sp);
+        if (multi && !fused_ar) SMB_TRY(dist_allreduce(d, S + S_PAP, S + S_PAP, 3, false));
+        SMB_TRY(cg_xr_launch(ctx, w, d->vt, x->d, n, nullptr, fused_ar ? d->ar_dev : nullptr));
+        if (multi && !fused_ar) SMB_TRY(dist_allreduce(d, S + S_RR_LOCAL, S + S_RR_NEW, 1, f32));     // r.r is a T in the reference: rounded like the single-GPU path
         return cg_p_launch(ctx, w, d->vt, n);
     };
     // the first iteration runs eagerly: it performs every lazy allocation / connection set-up outside of stream capture

@@ -118,6 +118,40 @@ __device__ __forceinline__ bool halo_wait(const HaloDev& h, unsigned long long e
     if (h.wait_stats) { atomicAdd(h.wait_stats, global_timer_ns() - t0); atomicAdd(h.wait_stats + 1, 1ull); }
     return true;
 }
+// All-reduce (sum) of `count` <= kArSlots doubles, executed by ONE converged warp inside any kernel: lane q < world stores
+// this rank's values (`mine[k]`, the same in every lane) into rank q's slot array and raises its flag, then waits for rank
+// q's values here; lane 0 adds the world's values in rank order (every rank computes the same bits) and returns them in
+// out[k].  sv: shared scratch [kMaxPeers][kArSlots].  Epochs alternate between two slot sets (a rank can be one all-reduce
+// ahead).  dist.cu's p2p_allreduce_kernel is this in a kernel of its own; the CG kernels call it in their last block.
+__device__ __forceinline__ void ar_warp_allreduce(const ArDev& a, const double* mine, double* out, int count, double (*sv)[kArSlots]) {
+    const unsigned long long e = __ldcg(a.epoch) + 1ull;
+    const int world = a.world, me = a.me, q = (int)(threadIdx.x & 31u);
+    const size_t par = (size_t)(e & 1ull);
+    if (q < world) {
+        double* dst = a.peer_vals[q] + (par * world + me) * kArSlots;
+        for (int k = 0; k < count; ++k) dst[k] = mine[k];
+        __threadfence_system();
+        st_release_sys(a.peer_flags[q] + par * world + me, e);
+        const unsigned long long* f = a.flags + par * world + q;
+        const unsigned long long t0 = global_timer_ns();
+        unsigned spins = 0;
+        while (ld_acquire_sys(f) < e) {
+            if ((++spins & 255u) == 0 && global_timer_ns() - t0 > a.timeout_ns) { atomicExch(a.error, 1u); break; }
+        }
+        const double* src = a.vals + (par * world + q) * kArSlots;
+        for (int k = 0; k < count; ++k) sv[q][k] = __ldcg(src + k);
+    }
+    __syncwarp();
+    if (q == 0) {
+        for (int k = 0; k < count; ++k) {
+            double sum = 0.0;
+            for (int r = 0; r < world; ++r) sum += sv[r][k];
+            out[k] = sum;
+        }
+        *a.epoch = e;
+    }
+    __syncwarp();
+}
 #endif
 
 }  // namespace smb

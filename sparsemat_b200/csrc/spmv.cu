@@ -57,6 +57,8 @@ struct DotArgs {
     double* roll_dst;
     const double* roll_src;
     const double* done;
+    // distributed CG (dist.cu): the finalize kernel also sums the ranks' totals through peer memory (halo.cuh)
+    const ArDev* ar;
 };
 
 template <class T> __device__ __forceinline__ T warp_sum_t(T v) {
@@ -86,12 +88,23 @@ __device__ __forceinline__ void finish_dot(double acc, const DotArgs& d) {
 constexpr int kFinalizeThreads = 1024;
 __global__ void __launch_bounds__(kFinalizeThreads)
 spmv_dot_finalize_kernel(const double* __restrict__ partials, unsigned n, int is_f32, double* __restrict__ result,
-                         double* __restrict__ roll_dst, const double* __restrict__ roll_src, const double* __restrict__ done) {
+                         double* __restrict__ roll_dst, const double* __restrict__ roll_src, const double* __restrict__ done,
+                         const ArDev* __restrict__ ar) {
     __shared__ double scratch[kFinalizeThreads / 32 + 1];
+    __shared__ double ar_sv[kMaxPeers][kArSlots], ar_in[kArSlots], ar_out[kArSlots];
     if (done != nullptr && __ldcg(done) != 0.0) return;      // the SpMV CTAs left early: keep the previous values
     double acc = 0.0;
     for (unsigned i = threadIdx.x; i < n; i += kFinalizeThreads) acc += __ldcg(partials + i);
-    const double total = block_sum<kFinalizeThreads>(acc, scratch);
+    double total = block_sum<kFinalizeThreads>(acc, scratch);
+    if (ar != nullptr) {
+        // one rank per GPU: the ranks' totals are exchanged through peer memory right here (every rank runs this kernel at
+        // the same point of its stream; the stop flag above is identical on all ranks), summed in rank order
+        if (threadIdx.x == 0) ar_in[0] = total;
+        __syncthreads();
+        if (threadIdx.x < 32) ar_warp_allreduce(*ar, ar_in, ar_out, 1, ar_sv);
+        __syncthreads();
+        total = ar_out[0];
+    }
     if (threadIdx.x == 0) {
         *result = is_f32 ? (double)(float)total : total;
         if (roll_dst) *roll_dst = *roll_src;
@@ -2122,7 +2135,7 @@ static smb200_status launch_typed(smb200_crs* m, const SpmvPlan& p, uint64_t rb,
                 SMB_CUDA(cudaGetLastError());
                 if constexpr (DOT) {
                     spmv_dot_finalize_kernel<<<1, kFinalizeThreads, 0, st>>>(d2.partials, g_last_pipe_grid, sizeof(T) == 4 ? 1 : 0, d2.result,
-                                                                           d2.roll_dst, d2.roll_src, d2.done);
+                                                                           d2.roll_dst, d2.roll_src, d2.done, d2.ar);
                     count_launch();
                     SMB_CUDA(cudaGetLastError());
                 }
@@ -2214,7 +2227,7 @@ static smb200_status launch_typed(smb200_crs* m, const SpmvPlan& p, uint64_t rb,
         else if (p.variant == SMB200_SPMV_STREAM_PIPE || p.variant == SMB200_SPMV_RING) n_partials = g_last_pipe_grid;
         else n_partials = (unsigned)p.n_blocks;
         spmv_dot_finalize_kernel<<<1, kFinalizeThreads, 0, st>>>(dot.partials, n_partials, sizeof(T) == 4 ? 1 : 0, dot.result,
-                                                               dot.roll_dst, dot.roll_src, dot.done);
+                                                               dot.roll_dst, dot.roll_src, dot.done, dot.ar);
         count_launch();
         SMB_CUDA(cudaGetLastError());
     }
@@ -2271,7 +2284,7 @@ static smb200_status spmv_launch_impl(smb200_crs* m, const SpmvPlan& p, uint64_t
         return SMB200_OK;
     }
     smb200_ctx* ctx = m->ctx;
-    DotArgs dot{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    DotArgs dot{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     if (w) {
         uint64_t blocks = p.variant >= SMB200_SPMV_STREAM ? p.n_blocks : ((re - rb) * (uint64_t)p.lanes + kSpmvThreads - 1) / kSpmvThreads;
         double* partials = ctx->red_partials;
@@ -2282,7 +2295,7 @@ static smb200_status spmv_launch_impl(smb200_crs* m, const SpmvPlan& p, uint64_t
             SMB_TRY(ensure_reduction_scratch(ctx, blocks));
             partials = ctx->red_partials;
         }
-        dot = DotArgs{w, partials, ctx->red_ticket, result, roll_dst, roll_src, done};
+        dot = DotArgs{w, partials, ctx->red_ticket, result, roll_dst, roll_src, done, g_dot_ar};
     }
     static thread_local const void* window_on = nullptr;
     if (p.flags & SMB200_FLAG_L2_PERSIST_X) {
