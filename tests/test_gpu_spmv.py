@@ -473,3 +473,32 @@ def test_value_indexing_is_exact_and_optional(smb, orc, ctx):
     d = smb.SparseMatCRS.from_raw_parts(ctx, N, N, v4, cols, offs)
     assert d.plan_info()["nnz_v8"] == 0
     assert np.array_equal(d.mvp(xd).to_numpy(), orc.mvp(v4, cols, offs, x))
+
+
+def test_l2_persisting_window_over_x(smb, orc, ctx):
+    """SMB200_FLAG_L2_PERSIST_X: an L2 access-policy window (persisting) over x for kernels that gather it from global memory.
+    A cache policy only: the same bits with the window on, after switching it off again, and on a second matrix whose x
+    lives elsewhere (the window follows the operand)."""
+    case = cases.ragged(91, 20000, 300000, 24, F64, U32)
+    n_rows, n_cols, vals, cols, offs = case
+    x = orc.uniform(F64, 4, n_cols)
+    want = orc.mvp(vals, cols, offs, x)
+    a = smb.SparseMatCRS.from_raw_parts(ctx, *case)
+    xd = smb.DenseVec.from_vec(ctx, x)
+    for variant in (smb.SPMV_STREAM, smb.SPMV_SCALAR):
+        a.configure(variant, 0, smb.FLAG_L2_PERSIST_X)
+        assert a.plan_info()["flags"] & smb.FLAG_L2_PERSIST_X
+        assert np.array_equal(a.mvp(xd).to_numpy(), want)
+        assert np.array_equal(a.mvp(xd).to_numpy(), want)                    # the window is already set: reused
+        x2 = smb.DenseVec.from_vec(ctx, x)                                   # another x: the window moves
+        assert np.array_equal(a.mvp(x2).to_numpy(), want)
+        a.configure(variant, 0, 0)
+        assert not (a.plan_info()["flags"] & smb.FLAG_L2_PERSIST_X)
+        assert np.array_equal(a.mvp(xd).to_numpy(), want)                    # window cleared
+    # a second matrix without the flag right after one with it: no stale window
+    a.configure(smb.SPMV_STREAM, 0, smb.FLAG_L2_PERSIST_X)
+    a.mvp(xd)
+    b = smb.SparseMatCRS.laplace(ctx, F64, U32, 20, 20, 20)
+    xb = orc.uniform(F64, 5, 8000)
+    vb, cb, ob = orc.laplace(F64, U32, 20, 20, 20)
+    assert np.array_equal(b.mvp(smb.DenseVec.from_vec(ctx, xb)).to_numpy(), orc.mvp(vb, cb, ob, xb))
