@@ -1761,7 +1761,7 @@ static smb200_status ring_sell_build(smb200_crs* m, SpmvPlan& p) {
     cudaMemsetAsync(p.sell_soff, 0, 4 * S + kPadBytes, st);
     const unsigned long long g0 = m->x_extra ? ((m->n_rows + 63) & ~(uint64_t)63) : ~0ull;     // dist.cu: ghosts from n_rows rounded up to 64
     sell_fill_kernel<I><<<(unsigned)n, 256, 0, st>>>((const I*)m->offsets, (const I*)p.blk_rows, d_w, d_sb, d_sz, d_sz + n, d_sz + 2 * n,
-                                                    p.vcodes, p.lcols, p.lcols_base, p.seg_lo, p.seg_len, g0, p.sell_codes, p.sell_cols,
+                                                    p.vcodes, p.lcols, p.lcols_base, (unsigned)ts, p.seg_lo, p.seg_len, g0, p.sell_codes, p.sell_cols,
                                                     p.sell_rowlen, p.sell_soff, (SellBlock*)p.sell_blocks);
     count_launch();
     SELL_CUDA(cudaGetLastError());

@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(256)
 sell_fill_kernel(const I* __restrict__ offs, const I* __restrict__ blk_rows, const unsigned* __restrict__ widths,
                  const unsigned long long* __restrict__ slice_base, const unsigned long long* __restrict__ ebase,
                  const unsigned long long* __restrict__ rbase, const unsigned long long* __restrict__ sbase,
-                 const uint8_t* __restrict__ vcodes, const uint16_t* __restrict__ lcols, unsigned long long codes_base,
+                 const uint8_t* __restrict__ vcodes, const uint16_t* __restrict__ lcols, unsigned long long codes_base, unsigned vbytes,
                  const unsigned long long* __restrict__ seg_lo, const unsigned* __restrict__ seg_len, unsigned long long g0,
                  uint8_t* __restrict__ s_codes, uint16_t* __restrict__ s_cols, uint8_t* __restrict__ s_rowlen, unsigned* __restrict__ s_soff,
                  SellBlock* __restrict__ blocks) {
@@ -111,7 +111,9 @@ sell_fill_kernel(const I* __restrict__ offs, const I* __restrict__ blk_rows, con
         const unsigned long long dst = ebase[b] + soff[q] + lane;
         for (unsigned long long k = ka; k < ke; ++k) {
             s_codes[dst + 32ull * (k - ka)] = vcodes[k - codes_base];
-            s_cols[dst + 32ull * (k - ka)] = lcols[k - codes_base];
+            // the window position as a BYTE offset into the staged x windows (they live inside a 55 KB stage, so it fits 16 bits):
+            // the consumers' gather then needs no address arithmetic
+            s_cols[dst + 32ull * (k - ka)] = (uint16_t)((unsigned)lcols[k - codes_base] * vbytes);
         }
     }
 }
@@ -243,21 +245,38 @@ spmv_ring_sell_kernel(const SellBlock* __restrict__ blocks, const uint8_t* __res
                 const uint8_t* pc = sc + off + lane;
                 const uint16_t* pp = sp + off + lane;
                 // two entries per trip, all four index loads first, then the four operand loads; the trip count is the slice's
-                // width (warp-uniform), a lane's own length only predicates the additions (padding is loaded, never added).
-                // Hand-shaped: the compiler's own unrolling of the simple loop cost 150 instructions per 7-entry slice.
+                // width (warp-uniform).  Positions are byte offsets into the staged windows.  When every row of the slice has the
+                // slice's width (the common case) nothing is predicated; otherwise a lane's own length predicates the additions
+                // (padding is loaded, never added).  Hand-shaped: the compiler's own unrolling of the simple loop cost 150
+                // instructions per 7-entry slice.
+                const unsigned char* sxb = reinterpret_cast<const unsigned char*>(sx);
                 unsigned j = 0;
+                if (__all_sync(0xffffffffu, len == w)) {
 #pragma unroll 1
-                for (; j + 2 <= w; j += 2) {
-                    const unsigned c0 = pc[0], p0 = pp[0], c1 = pc[32], p1 = pp[32];
-                    pc += 64; pp += 64;
-                    const T x0 = sx[p0], d0 = dict[c0], x1 = sx[p1], d1 = dict[c1];
-                    if (j < len) sum = add_rn(sum, mul_rn(x0, d0));
-                    if (j + 1 < len) sum = add_rn(sum, mul_rn(x1, d1));
-                }
-                if (j < w) {
-                    const unsigned c0 = pc[0], p0 = pp[0];
-                    const T x0 = sx[p0], d0 = dict[c0];
-                    if (j < len) sum = add_rn(sum, mul_rn(x0, d0));
+                    for (; j + 2 <= w; j += 2) {
+                        const unsigned c0 = pc[0], p0 = pp[0], c1 = pc[32], p1 = pp[32];
+                        pc += 64; pp += 64;
+                        const T x0 = *reinterpret_cast<const T*>(sxb + p0), d0 = dict[c0];
+                        const T x1 = *reinterpret_cast<const T*>(sxb + p1), d1 = dict[c1];
+                        sum = add_rn(sum, mul_rn(x0, d0));
+                        sum = add_rn(sum, mul_rn(x1, d1));
+                    }
+                    if (j < w) sum = add_rn(sum, mul_rn(*reinterpret_cast<const T*>(sxb + pp[0]), dict[pc[0]]));
+                } else {
+#pragma unroll 1
+                    for (; j + 2 <= w; j += 2) {
+                        const unsigned c0 = pc[0], p0 = pp[0], c1 = pc[32], p1 = pp[32];
+                        pc += 64; pp += 64;
+                        const T x0 = *reinterpret_cast<const T*>(sxb + p0), d0 = dict[c0];
+                        const T x1 = *reinterpret_cast<const T*>(sxb + p1), d1 = dict[c1];
+                        if (j < len) sum = add_rn(sum, mul_rn(x0, d0));
+                        if (j + 1 < len) sum = add_rn(sum, mul_rn(x1, d1));
+                    }
+                    if (j < w) {
+                        const unsigned c0 = pc[0], p0 = pp[0];
+                        const T x0 = *reinterpret_cast<const T*>(sxb + p0), d0 = dict[c0];
+                        if (j < len) sum = add_rn(sum, mul_rn(x0, d0));
+                    }
                 }
                 if (live) {
                     y[d.r0 + row] = sum;
