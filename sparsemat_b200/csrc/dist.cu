@@ -344,7 +344,7 @@ static smb200_status dist_p2p_setup(smb200_dist* d) {
     if (!all || fails != 0.0) { dist_p2p_release(d); return SMB200_OK; }
 
     const char* tenv = getenv("SMB200_P2P_TIMEOUT_MS");
-    const unsigned long long timeout_ns = (unsigned long long)(tenv ? atof(tenv) : 10000.0) * 1000000ull;
+    const unsigned long long timeout_ns = (unsigned long long)(tenv ? atof(tenv) : 30000.0) * 1000000ull;     // 30 s: host-side skew between ranks is not an error
     unsigned char* misc = (unsigned char*)d->misc;
     HaloDev h;
     memset(&h, 0, sizeof h);
