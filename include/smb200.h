@@ -352,8 +352,15 @@ smb200_status smb200_dist_barrier(smb200_dist* d);
  * distributed products completed, 1 if a peer wait timed out, sum of the spin times of all threads that
  * waited for a neighbour's flag in ns, number of such waits}.  Synchronises the context stream. */
 smb200_status smb200_dist_info(smb200_dist* d, uint64_t* out6);
+/* ConjugateGradient::solve (linearsolver.rs:27-61) over the row blocks: the reference's loop, two all-reduces
+ * (p.Ap, r.r) per iteration, both inside the kernels that produce their operands on the peer-memory path. */
 smb200_status smb200_dist_cg_solve(smb200_dist* d, const smb200_vec* b, smb200_vec* x, double tol, int32_t relative,
                                    uint64_t iter_max, smb200_cg_stats* stats);
+/* Additive: the same solve with the loop rearranged (Chronopoulos-Gear) so that r.r and (A r).r come out of
+ * ONE all-reduce per iteration; s = A p and alpha follow by recurrence.  Same arguments, stop test, history
+ * and vector traffic; the iteration count may differ from the reference's loop by a few. */
+smb200_status smb200_dist_cg_solve_sr(smb200_dist* d, const smb200_vec* b, smb200_vec* x, double tol, int32_t relative,
+                                      uint64_t iter_max, smb200_cg_stats* stats);
 
 #ifdef __cplusplus
 }

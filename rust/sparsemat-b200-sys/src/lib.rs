@@ -179,4 +179,6 @@ extern "C" {
     pub fn smb200_dist_info(d: *mut smb200_dist, out6: *mut u64) -> smb200_status;
     pub fn smb200_dist_cg_solve(d: *mut smb200_dist, b: *const smb200_vec, x: *mut smb200_vec, tol: f64, relative: i32,
                                 iter_max: u64, stats: *mut smb200_cg_stats) -> smb200_status;
+    pub fn smb200_dist_cg_solve_sr(d: *mut smb200_dist, b: *const smb200_vec, x: *mut smb200_vec, tol: f64, relative: i32,
+                                   iter_max: u64, stats: *mut smb200_cg_stats) -> smb200_status;
 }

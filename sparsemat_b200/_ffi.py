@@ -153,6 +153,7 @@ PROTOTYPES = {
     "smb200_dist_barrier": (_i32, [_p]),
     "smb200_dist_info": (_i32, [_p, _u64p]),
     "smb200_dist_cg_solve": (_i32, [_p, _p, _p, C.c_double, _i32, _u64, C.POINTER(CgStats)]),
+    "smb200_dist_cg_solve_sr": (_i32, [_p, _p, _p, C.c_double, _i32, _u64, C.POINTER(CgStats)]),
     # smb200_host.h
     "smb200_il_create": (_i32, [_i32, _i32, _pp]),
     "smb200_il_free": (_i32, [_p]),

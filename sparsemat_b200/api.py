@@ -524,10 +524,11 @@ def crs_from_indexlist_arrays(ctx, n_rows, n_cols, columns, values, pos_start, i
 
 
 class ConjugateGradient:
-    """linearsolver.rs:12-61.  ``ConjugateGradient()`` is ``Default``: tol 1e-12 (absolute), 10 000 iterations."""
+    """linearsolver.rs:12-61.  ``ConjugateGradient()`` is ``Default``: tol 1e-12 (absolute), 10 000 iterations.
+    ``single_reduce`` (additive, distributed matrices only): the loop rearranged so that an iteration has one all-reduce."""
 
-    def __init__(self, tol: float = 1e-12, iter_max: int = 10_000, relative: bool = False):
-        self.tol, self.iter_max, self.relative = tol, iter_max, relative
+    def __init__(self, tol: float = 1e-12, iter_max: int = 10_000, relative: bool = False, single_reduce: bool = False):
+        self.tol, self.iter_max, self.relative, self.single_reduce = tol, iter_max, relative, single_reduce
         self.last_stats = None
 
     @classmethod
@@ -539,8 +540,11 @@ class ConjugateGradient:
 
     def solve_with_stats(self, mat, b: DenseVec, x: DenseVec) -> dict:
         st = F.CgStats()
+        if self.single_reduce and not isinstance(mat, DistCRS):
+            raise ValueError("single_reduce is the distributed solver's option (DistCRS)")
         if isinstance(mat, DistCRS):
-            check(lib.smb200_dist_cg_solve(mat._h, b._h, x._h, self.tol, int(self.relative), self.iter_max, C.byref(st)))
+            fn = lib.smb200_dist_cg_solve_sr if self.single_reduce else lib.smb200_dist_cg_solve
+            check(fn(mat._h, b._h, x._h, self.tol, int(self.relative), self.iter_max, C.byref(st)))
         else:
             check(lib.smb200_cg_solve(mat._h, b._h, x._h, self.tol, int(self.relative), self.iter_max, C.byref(st)))
         self.last_stats = {"iterations": st.iterations, "final_residual": st.final_residual,

@@ -15,6 +15,7 @@
 // stop test fires the remaining kernels of a batch exit immediately, leaving x, r, p untouched — the
 // reference's `break` (linearsolver.rs:52-54).
 #include "common.cuh"
+#include "cg_sr.cuh"
 #include "halo.cuh"
 #include "reduce.cuh"
 
@@ -206,10 +207,86 @@ cg_update_p_kernel(T* __restrict__ p, const T* __restrict__ r, uint64_t n, doubl
     for (uint64_t i = nvec * N + tid; i < n; i += stride) p[i] = add_rn(mul_rn(p[i], beta), PRE ? mul_rn(dinv[i], r[i]) : r[i]);
 }
 
+
+// ---- single-reduction variant (cg_sr.cuh) ------------------------------------------------------------
+// U: p = r + (p * beta); s = w + (s * beta); x += (p * alpha); r -= (s * alpha); S[RR_NEW] = r.r of this rank (f64, unrounded)
+template <class T>
+__global__ void __launch_bounds__(kCgThreads)
+cgsr_update_kernel(T* __restrict__ x, T* __restrict__ r, T* __restrict__ p, T* __restrict__ s, const T* __restrict__ w, uint64_t n,
+                   double* __restrict__ S, double* __restrict__ partials, unsigned int* __restrict__ ticket, int vec_ok) {
+    __shared__ double scratch[kCgThreads / 32 + 1];
+    if (__ldcg(S + S_DONE) != 0.0) return;
+    const T alpha = (T)__ldcg(S + SR_ALPHA), beta = (T)__ldcg(S + SR_BETA);
+    const bool first = beta == T(0);           // p = r, s = w whatever an earlier solve left in p and s
+    using V = typename Vec16<T>::type;
+    constexpr int N = Vec16<T>::N;
+    const uint64_t tid = blockIdx.x * (uint64_t)kCgThreads + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * kCgThreads;
+    const uint64_t nvec = vec_ok ? n / N : 0;
+    T lane_acc[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) lane_acc[k] = T(0);
+    for (uint64_t i = tid; i < nvec; i += stride) {
+        Pack16<T> px, pr, pp, ps, pw;
+        pw.v = __ldg(reinterpret_cast<const V*>(w) + i);
+        pr.v = reinterpret_cast<V*>(r)[i];
+        if (!first) { pp.v = reinterpret_cast<V*>(p)[i]; ps.v = reinterpret_cast<V*>(s)[i]; }
+        px.v = reinterpret_cast<V*>(x)[i];
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            pp.e[k] = first ? pr.e[k] : add_rn(pr.e[k], mul_rn(pp.e[k], beta));
+            ps.e[k] = first ? pw.e[k] : add_rn(pw.e[k], mul_rn(ps.e[k], beta));
+            px.e[k] = add_rn(px.e[k], mul_rn(pp.e[k], alpha));
+            pr.e[k] = sub_rn(pr.e[k], mul_rn(ps.e[k], alpha));
+            lane_acc[k] = add_rn(lane_acc[k], mul_rn(pr.e[k], pr.e[k]));
+        }
+        reinterpret_cast<V*>(p)[i] = pp.v;
+        reinterpret_cast<V*>(s)[i] = ps.v;
+        reinterpret_cast<V*>(x)[i] = px.v;
+        reinterpret_cast<V*>(r)[i] = pr.v;
+    }
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < N; ++k) acc += (double)lane_acc[k];
+    for (uint64_t i = nvec * N + tid; i < n; i += stride) {
+        const T rv0 = r[i];
+        const T pv = first ? rv0 : add_rn(rv0, mul_rn(p[i], beta));
+        const T sv = first ? w[i] : add_rn(w[i], mul_rn(s[i], beta));
+        p[i] = pv; s[i] = sv;
+        x[i] = add_rn(x[i], mul_rn(pv, alpha));
+        const T rv = sub_rn(rv0, mul_rn(sv, alpha));
+        r[i] = rv;
+        acc += (double)mul_rn(rv, rv);
+    }
+    const double bsum = block_sum<kCgThreads>(acc, scratch);
+    double total;
+    if (grid_sum<kCgThreads>(bsum, partials, ticket, scratch, total))
+        if (threadIdx.x == 0) S[S_RR_NEW] = total;
+}
+
+// S in a kernel of its own (one warp): local plans whose product is more than one launch, and the NCCL fallback (the host
+// has all-reduced S[1..4] in front of it: ar == nullptr).
+template <class T>
+__global__ void __launch_bounds__(32)
+cgsr_scalar_kernel(double* __restrict__ S, const ArDev* __restrict__ ar, double* __restrict__ history, unsigned long long hist_cap) {
+    __shared__ double ar_sv[kMaxPeers][kArSlots], ar_in[kArSlots], ar_out[kArSlots];
+    if (__ldcg(S + S_DONE) != 0.0) return;
+    if (threadIdx.x == 0) {
+        ar_in[0] = __ldcg(S + S_PAP) + __ldcg(S + S_PAP + 1) + __ldcg(S + S_PAP + 2);
+        ar_in[1] = __ldcg(S + S_RR_NEW);
+        ar_out[0] = ar_in[0]; ar_out[1] = ar_in[1];
+    }
+    __syncwarp();
+    if (ar != nullptr) ar_warp_allreduce(*ar, ar_in, ar_out, 2, ar_sv);
+    __syncwarp();
+    if (threadIdx.x == 0) cgsr_scalars<T>(S, ar_out[0], ar_out[1], history, hist_cap);
+}
+
 void cg_free(CgWork& w) {
     if (w.r) cudaFree(w.r);
     if (w.p) cudaFree(w.p);
     if (w.ap) cudaFree(w.ap);
+    if (w.s) cudaFree(w.s);
     if (w.scalars) cudaFree(w.scalars);
     if (w.scalars_host) cudaFreeHost(w.scalars_host);
     if (w.history) cudaFree(w.history);
@@ -227,12 +304,14 @@ static unsigned cg_grid(const smb200_ctx* ctx, uint64_t n, int vt) {
 
 // p_cap: allocated elements of p (dist solves keep ghost room behind the owned part)
 smb200_status cg_prepare(smb200_ctx* ctx, CgWork& w, int vt, uint64_t n, uint64_t p_cap, uint64_t iter_max) {
-    if (w.n != n || !w.r || w.hist_cap < (iter_max < (1u << 20) ? iter_max : (1u << 20))) {
+    if (w.n != n || !w.r || w.cap < (p_cap > n ? p_cap : n) || w.hist_cap < (iter_max < (1u << 20) ? iter_max : (1u << 20))) {
         cudaStreamSynchronize(ctx->stream);
         cg_free(w);
         const size_t es = vsize(vt);
-        SMB_TRY(dev_alloc(&w.r, n * es));
+        SMB_TRY(dev_alloc(&w.r, (p_cap > n ? p_cap : n) * es));     // the single-reduction variant multiplies r: ghost room like p
         SMB_TRY(dev_alloc(&w.p, (p_cap > n ? p_cap : n) * es));
+        SMB_CUDA(cudaMemsetAsync(w.r, 0, (p_cap > n ? p_cap : n) * es + kPadBytes, ctx->stream));
+        w.cap = p_cap > n ? p_cap : n;
         SMB_TRY(dev_alloc(&w.ap, n * es));
         SMB_CUDA(cudaMemsetAsync(w.p, 0, (p_cap > n ? p_cap : n) * es + kPadBytes, ctx->stream));
         SMB_CUDA(cudaMalloc(&w.scalars, S_COUNT * sizeof(double)));
@@ -246,9 +325,9 @@ smb200_status cg_prepare(smb200_ctx* ctx, CgWork& w, int vt, uint64_t n, uint64_
     return SMB200_OK;
 }
 
-smb200_status cg_init_launch(smb200_ctx* ctx, CgWork& w, int vt, const void* b, uint64_t n, const void* dinv) {
+smb200_status cg_init_launch(smb200_ctx* ctx, CgWork& w, int vt, const void* b, uint64_t n, const void* dinv, int rr_slot) {
     const unsigned g = cg_grid(ctx, n, vt);
-    const int slot = ctx->world > 1 ? S_RR_LOCAL : S_RR_NEW;
+    const int slot = rr_slot >= 0 ? rr_slot : ctx->world > 1 ? S_RR_LOCAL : S_RR_NEW;
     const int vec_ok = ((uintptr_t)b & 15u) == 0 ? 1 : 0;
     if (dinv) {
         if (vt == SMB200_F64) cg_init_kernel<double, true><<<g, kCgThreads, 0, ctx->stream>>>((const double*)b, (const double*)w.ap, (double*)w.r, (double*)w.p, n, w.scalars, slot, ctx->red_partials, ctx->red_ticket, vec_ok, (const double*)dinv);
@@ -281,6 +360,33 @@ smb200_status cg_p_launch(smb200_ctx* ctx, CgWork& w, int vt, uint64_t n, const 
         else cg_update_p_kernel<float, true><<<g, kCgThreads, 0, ctx->stream>>>((float*)w.p, (const float*)w.r, n, w.scalars, w.history, w.hist_cap, (const float*)dinv);
     } else if (vt == SMB200_F64) cg_update_p_kernel<double, false><<<g, kCgThreads, 0, ctx->stream>>>((double*)w.p, (const double*)w.r, n, w.scalars, w.history, w.hist_cap, nullptr);
     else cg_update_p_kernel<float, false><<<g, kCgThreads, 0, ctx->stream>>>((float*)w.p, (const float*)w.r, n, w.scalars, w.history, w.hist_cap, nullptr);
+    count_launch();
+    SMB_CUDA(cudaGetLastError());
+    return SMB200_OK;
+}
+
+// single-reduction variant: the workspace's fourth vector, allocated when first needed
+smb200_status cgsr_prepare(smb200_ctx* ctx, CgWork& w, int vt) {
+    if (!w.s) {
+        SMB_TRY(dev_alloc(&w.s, w.cap * vsize(vt)));
+        SMB_CUDA(cudaMemsetAsync(w.s, 0, w.cap * vsize(vt), ctx->stream));
+    }
+    return SMB200_OK;
+}
+
+smb200_status cgsr_update_launch(smb200_ctx* ctx, CgWork& w, int vt, void* x, uint64_t n) {
+    const unsigned g = cg_grid(ctx, n, vt);
+    const int vec_ok = ((uintptr_t)x & 15u) == 0 ? 1 : 0;
+    if (vt == SMB200_F64) cgsr_update_kernel<double><<<g, kCgThreads, 0, ctx->stream>>>((double*)x, (double*)w.r, (double*)w.p, (double*)w.s, (const double*)w.ap, n, w.scalars, ctx->red_partials, ctx->red_ticket, vec_ok);
+    else cgsr_update_kernel<float><<<g, kCgThreads, 0, ctx->stream>>>((float*)x, (float*)w.r, (float*)w.p, (float*)w.s, (const float*)w.ap, n, w.scalars, ctx->red_partials, ctx->red_ticket, vec_ok);
+    count_launch();
+    SMB_CUDA(cudaGetLastError());
+    return SMB200_OK;
+}
+
+smb200_status cgsr_scalar_launch(smb200_ctx* ctx, CgWork& w, int vt, const ArDev* ar) {
+    if (vt == SMB200_F64) cgsr_scalar_kernel<double><<<1, 32, 0, ctx->stream>>>(w.scalars, ar, w.history, w.hist_cap);
+    else cgsr_scalar_kernel<float><<<1, 32, 0, ctx->stream>>>(w.scalars, ar, w.history, w.hist_cap);
     count_launch();
     SMB_CUDA(cudaGetLastError());
     return SMB200_OK;
@@ -386,6 +492,7 @@ smb200_status cg_solve_impl(smb200_crs* a, const smb200_vec* b, smb200_vec* x, d
                     w.graph_partials = ctx->red_partials;
                     w.graph_plan = a->plan.blk_rows;
                     w.graph_dinv = dinv;
+                    w.graph_kind = 0;
                 }
                 e = cudaGraphLaunch(w.graph, ctx->stream);
                 if (e != cudaSuccess) { set_error("cg_solve: graph launch failed: %s", cudaGetErrorString(e)); st = SMB200_ERR_CUDA; break; }

@@ -167,6 +167,8 @@ struct HostPipe {
 struct CgWork {
     uint64_t n = 0;
     void* r = nullptr; void* p = nullptr; void* ap = nullptr;
+    void* s = nullptr;                  // single-reduction variant (cg_sr.cuh): s = A p by recurrence
+    uint64_t cap = 0;                   // allocated elements of r, p, s (>= n: ghost room in distributed solves)
     double* scalars = nullptr;          // device: see cg.cu
     double* scalars_host = nullptr;     // pinned mirror
     double* history = nullptr;          // device [hist_cap]
@@ -177,6 +179,7 @@ struct CgWork {
     const void* graph_x = nullptr;      // pointers the graph was captured with
     const void* graph_partials = nullptr;
     const void* graph_plan = nullptr;
+    int graph_kind = 0;                 // 0: the reference's loop, 1: single-reduction
     const void* graph_dinv = nullptr;   // Jacobi-preconditioned batch: the inverse diagonal it was captured with
     void* dinv = nullptr;               // 1 / diag(A) of the last preconditioned solve (n elements)
     uint64_t dinv_n = 0;
@@ -256,7 +259,10 @@ smb200_status gen_laplace_block(smb200_ctx* ctx, int vt, int it, uint64_t nx, ui
                                 uint64_t row_hi, int local_cols, uint64_t n_lo_ghost, uint64_t n_cols_out,
                                 smb200_crs** out, uint64_t ghost_base = 0);   // ghost_base 0: ghosts right behind the owned columns
 smb200_status cg_prepare(smb200_ctx* ctx, CgWork& w, int vt, uint64_t n, uint64_t p_cap, uint64_t iter_max);
-smb200_status cg_init_launch(smb200_ctx* ctx, CgWork& w, int vt, const void* b, uint64_t n, const void* dinv = nullptr);
+smb200_status cg_init_launch(smb200_ctx* ctx, CgWork& w, int vt, const void* b, uint64_t n, const void* dinv = nullptr, int rr_slot = -1);
+smb200_status cgsr_prepare(smb200_ctx* ctx, CgWork& w, int vt);
+smb200_status cgsr_update_launch(smb200_ctx* ctx, CgWork& w, int vt, void* x, uint64_t n);
+smb200_status cgsr_scalar_launch(smb200_ctx* ctx, CgWork& w, int vt, const ArDev* ar);
 smb200_status cg_xr_launch(smb200_ctx* ctx, CgWork& w, int vt, void* x, uint64_t n, const void* dinv = nullptr, const ArDev* ar = nullptr);
 smb200_status cg_p_launch(smb200_ctx* ctx, CgWork& w, int vt, uint64_t n, const void* dinv = nullptr);
 smb200_status cg_solve_impl(smb200_crs* a, const smb200_vec* b, smb200_vec* x, double tol, int32_t relative,

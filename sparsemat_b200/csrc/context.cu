@@ -1,5 +1,6 @@
 // Context, events, host memory, error reporting.
 #include "common.cuh"
+#include "cg_sr.cuh"
 
 namespace smb {
 
@@ -13,6 +14,7 @@ thread_local bool g_spmv_band = false;
 thread_local bool g_x_unpadded = false;
 thread_local HaloLaunch g_halo;
 thread_local const ArDev* g_dot_ar = nullptr;
+thread_local CgSrLaunch g_cgsr;
 
 void set_error(const char* fmt, ...) {
     va_list ap;

@@ -18,6 +18,7 @@
 // NCCL is loaded with dlopen at smb200_comm_init time, so single-GPU users carry no NCCL dependency
 // and the library loads on machines without it.
 #include "common.cuh"
+#include "cg_sr.cuh"
 #include "halo.cuh"
 
 #include <dlfcn.h>
@@ -876,8 +877,11 @@ smb200_status smb200_dist_info(smb200_dist* d, uint64_t* out6) {
     return SMB200_OK;
 }
 
-smb200_status smb200_dist_cg_solve(smb200_dist* d, const smb200_vec* b, smb200_vec* x, double tol, int32_t relative,
-                                   uint64_t iter_max, smb200_cg_stats* stats) {
+}  // extern "C"
+
+// sr: the single-reduction rearrangement of the loop (cg_sr.cuh) instead of the reference's
+static smb200_status dist_cg_impl(smb200_dist* d, const smb200_vec* b, smb200_vec* x, double tol, int32_t relative,
+                                  uint64_t iter_max, smb200_cg_stats* stats, bool sr) {
     SMB_REQUIRE(d && b && x, SMB200_ERR_INVALID, "dist_cg_solve: NULL argument");
     SMB_REQUIRE(b->vt == d->vt && x->vt == d->vt, SMB200_ERR_INVALID, "dist_cg_solve: value types differ");
     SMB_REQUIRE(d->n_local == b->n && d->n_local == x->n, SMB200_ERR_SIZE_MISMATCH, "Matrix and vector size mismatch");
@@ -892,8 +896,9 @@ smb200_status smb200_dist_cg_solve(smb200_dist* d, const smb200_vec* b, smb200_v
     if (stats) memset(stats, 0, sizeof *stats);
     SMB_CUDA(cudaSetDevice(ctx->device));
     SMB_TRY(cg_prepare(ctx, w, d->vt, n, d->g0 + d->n_ghost, iter_max));
+    if (sr) SMB_TRY(cgsr_prepare(ctx, w, d->vt));
     double* S = w.scalars;
-    enum { S_RR = 0, S_PAP = 1, S_RR_NEW = 4, S_THRESH = 5, S_ITER = 6, S_DONE = 7, S_RR_LOCAL = 8, S_COUNT = 16 };   // cg.cu
+    enum { S_RR = 0, S_PAP = 1, S_RR_NEW = 4, S_THRESH = 5, S_ITER = 6, S_DONE = 7, S_RR_LOCAL = 8, S_RES2 = 9, S_COUNT = 16 };   // cg.cu
 
     double threshold = tol;
     if (relative) {
@@ -918,8 +923,8 @@ smb200_status smb200_dist_cg_solve(smb200_dist* d, const smb200_vec* b, smb200_v
     SMB_CUDA(cudaMemcpyAsync(S, w.scalars_host + 3 * S_COUNT, sizeof init, cudaMemcpyHostToDevice, ctx->stream));
     // r = b - A x ; p = r ; rr = r.r
     SMB_TRY(dist_spmv_impl(d, x->d, w.ap, nullptr));
-    SMB_TRY(cg_init_launch(ctx, w, d->vt, b->d, n));
-    if (multi) SMB_TRY(dist_allreduce(d, S + S_RR_LOCAL, S + S_RR_NEW, 1, f32));
+    SMB_TRY(cg_init_launch(ctx, w, d->vt, b->d, n, nullptr, sr ? S_RR_NEW : -1));
+    if (multi && !sr) SMB_TRY(dist_allreduce(d, S + S_RR_LOCAL, S + S_RR_NEW, 1, f32));
 
     const char* benv = getenv("SMB200_CG_BATCH");
     int batch = benv ? atoi(benv) : 8;
@@ -947,8 +952,31 @@ smb200_status smb200_dist_cg_solve(smb200_dist* d, const smb200_vec* b, smb200_v
         if (multi && !fused_ar) SMB_TRY(dist_allreduce(d, S + S_RR_LOCAL, S + S_RR_NEW, 1, f32));     // r.r is a T in the reference: rounded like the single-GPU path
         return cg_p_launch(ctx, w, d->vt, n);
     };
+    // Single-reduction iteration (cg_sr.cuh): vector update with the rank's r.r | halo exchange + w = A r with w.r fused |
+    // ONE all-reduce of the pair + the scalar step — inside the fused dot's finalize kernel when the product is one launch
+    // (three launches per iteration), else in a one-warp kernel behind it (NCCL fallback: ncclAllReduce in between).
+    const bool sr_fused = dist_exchanges(d) ? multi && d->p2p && a->plan.built && a->plan.variant == SMB200_SPMV_RING
+                                            : (!multi || d->p2p) && d->int_begin == 0 && d->int_end == d->n_local;   // no halo: plan_int is the product
+    auto sr_product = [&]() -> smb200_status {
+        if (!sr_fused && cudaMemsetAsync(S + S_PAP, 0, 3 * sizeof(double), ctx->stream) != cudaSuccess) { set_error("dist_cg_solve: memset failed"); return SMB200_ERR_CUDA; }
+        g_cgsr = CgSrLaunch{sr_fused ? S : nullptr, w.history, w.hist_cap, true};
+        g_dot_ar = sr_fused && multi ? d->ar_dev : nullptr;
+        const smb200_status sp = dist_spmv_impl(d, w.r, w.ap, S);
+        g_dot_ar = nullptr;
+        g_cgsr = CgSrLaunch();
+        SMB_TRY(sp);
+        if (sr_fused) return SMB200_OK;
+        if (multi && !d->p2p) SMB_TRY(dist_allreduce(d, S + S_PAP, S + S_PAP, 4, false));      // S_PAP..S_PAP+2, S_RR_NEW: contiguous
+        return cgsr_scalar_launch(ctx, w, d->vt, multi && d->p2p ? d->ar_dev : nullptr);
+    };
+    auto sr_iteration = [&]() -> smb200_status {
+        SMB_TRY(cgsr_update_launch(ctx, w, d->vt, x->d, n));
+        return sr_product();
+    };
+    if (sr) SMB_TRY(sr_product());          // w0 = A r0, alpha0 = r0.r0 / w0.r0, beta0 = 0
+    auto step = [&]() -> smb200_status { return sr ? sr_iteration() : iteration(); };
     // the first iteration runs eagerly: it performs every lazy allocation / connection set-up outside of stream capture
-    if (iter_max > 0) { st = iteration(); launched = 1; }
+    if (iter_max > 0) { st = step(); launched = 1; }
     while (st == SMB200_OK && !finished) {
         const int slot = (int)(rounds & 1);
         cudaError_t e = cudaMemcpyAsync(w.scalars_host + slot * S_COUNT, S, S_COUNT * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
@@ -958,12 +986,13 @@ smb200_status smb200_dist_cg_solve(smb200_dist* d, const smb200_vec* b, smb200_v
         if (nb == (uint64_t)batch && use_graph) {
             // a batch of iterations — kernels, NCCL send/recv and all-reduces on both streams — replayed from one CUDA graph,
             // so the host enqueues one node per batch instead of ~20 calls per iteration
-            if (!w.graph || w.graph_batch != batch || w.graph_x != x->d || w.graph_partials != ctx->red_partials || w.graph_plan != (const void*)d) {
+            if (!w.graph || w.graph_batch != batch || w.graph_x != x->d || w.graph_partials != ctx->red_partials || w.graph_plan != (const void*)d ||
+                w.graph_kind != (sr ? 1 : 0)) {
                 if (w.graph) { cudaGraphExecDestroy(w.graph); w.graph = nullptr; }
                 cudaGraph_t graph = nullptr;
                 e = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal);
                 if (e == cudaSuccess) {
-                    for (int k = 0; k < batch && st == SMB200_OK; ++k) st = iteration();
+                    for (int k = 0; k < batch && st == SMB200_OK; ++k) st = step();
                     cudaError_t e2 = cudaStreamEndCapture(ctx->stream, &graph);
                     if (st == SMB200_OK && e2 != cudaSuccess) e = e2;
                 }
@@ -972,11 +1001,12 @@ smb200_status smb200_dist_cg_solve(smb200_dist* d, const smb200_vec* b, smb200_v
                 if (e != cudaSuccess && st == SMB200_OK) { set_error("dist_cg_solve: graph capture failed: %s", cudaGetErrorString(e)); st = SMB200_ERR_CUDA; }
                 if (st != SMB200_OK) break;
                 w.graph_batch = batch; w.graph_x = x->d; w.graph_partials = ctx->red_partials; w.graph_plan = (const void*)d;
+                w.graph_kind = sr ? 1 : 0;
             }
             e = cudaGraphLaunch(w.graph, ctx->stream);
             if (e != cudaSuccess) { set_error("dist_cg_solve: graph launch failed: %s", cudaGetErrorString(e)); st = SMB200_ERR_CUDA; break; }
         } else {
-            for (uint64_t k = 0; k < nb && st == SMB200_OK; ++k) st = iteration();
+            for (uint64_t k = 0; k < nb && st == SMB200_OK; ++k) st = step();
         }
         if (st != SMB200_OK) break;
         launched += nb;
@@ -999,7 +1029,7 @@ smb200_status smb200_dist_cg_solve(smb200_dist* d, const smb200_vec* b, smb200_v
             cudaMemcpy(w.history_host.data(), w.history, w.history_host.size() * sizeof(double), cudaMemcpyDeviceToHost);
         if (stats) {
             stats->iterations = iters;
-            stats->final_residual = sqrt(H[S_RR_NEW]);
+            stats->final_residual = sqrt(sr ? H[S_RES2] : H[S_RR_NEW]);
             stats->converged = H[S_DONE] != 0.0;
             cudaEventElapsedTime(&stats->device_ms, ev0, ev1);
             stats->launches = g_launches - launches0;
@@ -1008,6 +1038,18 @@ smb200_status smb200_dist_cg_solve(smb200_dist* d, const smb200_vec* b, smb200_v
     }
     if (st != SMB200_OK) cudaStreamSynchronize(ctx->stream);
     return st;
+}
+
+extern "C" {
+
+smb200_status smb200_dist_cg_solve(smb200_dist* d, const smb200_vec* b, smb200_vec* x, double tol, int32_t relative,
+                                   uint64_t iter_max, smb200_cg_stats* stats) {
+    return dist_cg_impl(d, b, x, tol, relative, iter_max, stats, false);
+}
+
+smb200_status smb200_dist_cg_solve_sr(smb200_dist* d, const smb200_vec* b, smb200_vec* x, double tol, int32_t relative,
+                                      uint64_t iter_max, smb200_cg_stats* stats) {
+    return dist_cg_impl(d, b, x, tol, relative, iter_max, stats, true);
 }
 
 }  // extern "C"

@@ -24,6 +24,7 @@
 //          SMB200_FLAG_L2_PERSIST_X    L2 access-policy window over x for everything else.
 // Every variant can fuse a dot product  sum_r w[r]*y[r]  into its epilogue (K7a, used by CG).
 #include "common.cuh"
+#include "cg_sr.cuh"
 #include "halo.cuh"
 #include "reduce.cuh"
 
@@ -89,13 +90,26 @@ constexpr int kFinalizeThreads = 1024;
 __global__ void __launch_bounds__(kFinalizeThreads)
 spmv_dot_finalize_kernel(const double* __restrict__ partials, unsigned n, int is_f32, double* __restrict__ result,
                          double* __restrict__ roll_dst, const double* __restrict__ roll_src, const double* __restrict__ done,
-                         const ArDev* __restrict__ ar) {
+                         const ArDev* __restrict__ ar, CgSrLaunch sr) {
     __shared__ double scratch[kFinalizeThreads / 32 + 1];
     __shared__ double ar_sv[kMaxPeers][kArSlots], ar_in[kArSlots], ar_out[kArSlots];
     if (done != nullptr && __ldcg(done) != 0.0) return;      // the SpMV CTAs left early: keep the previous values
     double acc = 0.0;
     for (unsigned i = threadIdx.x; i < n; i += kFinalizeThreads) acc += __ldcg(partials + i);
     double total = block_sum<kFinalizeThreads>(acc, scratch);
+    if (sr.S != nullptr) {
+        // single-reduction CG (cg_sr.cuh): this product's (A r).r and the r.r the update kernel left travel in ONE
+        // all-reduce, and the iteration's scalar step runs right here
+        if (threadIdx.x == 0) { ar_in[0] = total; ar_in[1] = __ldcg(sr.S + 4); ar_out[0] = ar_in[0]; ar_out[1] = ar_in[1]; }
+        __syncthreads();
+        if (ar != nullptr && threadIdx.x < 32) ar_warp_allreduce(*ar, ar_in, ar_out, 2, ar_sv);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (is_f32) cgsr_scalars<float>(sr.S, ar_out[0], ar_out[1], sr.history, sr.hist_cap);
+            else cgsr_scalars<double>(sr.S, ar_out[0], ar_out[1], sr.history, sr.hist_cap);
+        }
+        return;
+    }
     if (ar != nullptr) {
         // one rank per GPU: the ranks' totals are exchanged through peer memory right here (every rank runs this kernel at
         // the same point of its stream; the stop flag above is identical on all ranks), summed in rank order
@@ -2135,7 +2149,7 @@ static smb200_status launch_typed(smb200_crs* m, const SpmvPlan& p, uint64_t rb,
                 SMB_CUDA(cudaGetLastError());
                 if constexpr (DOT) {
                     spmv_dot_finalize_kernel<<<1, kFinalizeThreads, 0, st>>>(d2.partials, g_last_pipe_grid, sizeof(T) == 4 ? 1 : 0, d2.result,
-                                                                           d2.roll_dst, d2.roll_src, d2.done, d2.ar);
+                                                                           d2.roll_dst, d2.roll_src, d2.done, d2.ar, g_cgsr);
                     count_launch();
                     SMB_CUDA(cudaGetLastError());
                 }
@@ -2227,7 +2241,7 @@ static smb200_status launch_typed(smb200_crs* m, const SpmvPlan& p, uint64_t rb,
         else if (p.variant == SMB200_SPMV_STREAM_PIPE || p.variant == SMB200_SPMV_RING) n_partials = g_last_pipe_grid;
         else n_partials = (unsigned)p.n_blocks;
         spmv_dot_finalize_kernel<<<1, kFinalizeThreads, 0, st>>>(dot.partials, n_partials, sizeof(T) == 4 ? 1 : 0, dot.result,
-                                                               dot.roll_dst, dot.roll_src, dot.done, dot.ar);
+                                                               dot.roll_dst, dot.roll_src, dot.done, dot.ar, g_cgsr);
         count_launch();
         SMB_CUDA(cudaGetLastError());
     }
@@ -2319,7 +2333,8 @@ smb200_status spmv_launch_plan(smb200_crs* m, const SpmvPlan& p, uint64_t rb, ui
 // (cg.cu: S_RR=0, S_PAP=1..3, S_RR_NEW=4, S_DONE=7).  `roll` makes the launch also do rr <- rr_new.
 smb200_status spmv_launch_cg(smb200_crs* m, const SpmvPlan& p, uint64_t rb, uint64_t re, const void* x, void* y,
                              const void* w, double* S, int slot, bool roll) {
-    return spmv_launch_impl(m, p, rb, re, x, y, w, S + 1 + slot, roll ? S + 0 : nullptr, S + 4, S + 7);
+    // single-reduction iterations (cg_sr.cuh) keep gamma in S[0] themselves: no roll
+    return spmv_launch_impl(m, p, rb, re, x, y, w, S + 1 + slot, roll && !g_cgsr.active ? S + 0 : nullptr, S + 4, S + 7);
 }
 
 smb200_status spmv_launch(smb200_crs* m, const void* x, void* y, const void* w, int dot_slot, uint64_t, uint64_t) {

@@ -155,6 +155,52 @@ def test_cg_matches_the_oracle_solver(smb, orc, ctx, vdt, tol, n):
         assert np.allclose(got, xo, rtol=0, atol=(1e-7 if vdt == np.float64 else 2e-2))
 
 
+@pytest.mark.parametrize("vdt,tol,n", [(np.float64, 1e-9, 40), (np.float32, 1e-4, 24)])
+def test_single_reduction_cg_tracks_the_oracle_solver(smb, orc, monkeypatch, vdt, tol, n):
+    """smb200_dist_cg_solve_sr on one rank: the loop of linearsolver.rs:41-60 rearranged so that r.r and (A r).r come out of
+    one reduction (additive — the reference has no such variant, so the check is against the oracle's plain CG: same
+    iteration count within 2 %, same residual history over the first iterations, same solution, true residual recomputed
+    by the oracle).  Without a halo the scalar step runs inside the fused dot's finalize kernel; SMB200_DIST_SELF=1 sends the
+    one rank through the distributed kernels (ring launch with the halo protocol, then push | rows | wait), where the
+    scalar step is the one-warp kernel behind the product."""
+    c = smb.Context(0)
+    c.comm_init(0, 1, None)
+    N = n ** 3
+    vals, cols, offs = orc.laplace(vdt, np.uint32, n, n, n)
+    b_h = orc.mvp(vals, cols, offs, orc.uniform(vdt, 6, N))
+    xo = np.zeros(N, vdt)
+    so = orc.cg(N, N, vals, cols, offs, b_h, xo, tol=tol, relative=True, iter_max=2000, history_cap=2000)
+    assert so["converged"]
+    for variant, self_halo in ((smb.SPMV_AUTO, "0"), (smb.SPMV_AUTO, "1"), (smb.SPMV_VECTOR, "1")):
+        monkeypatch.setenv("SMB200_DIST_SELF", self_halo)
+        a = smb.DistCRS.laplace(c, vdt, np.uint32, n, n, n)
+        assert a.info()["p2p"] == (self_halo == "1")
+        a.local.configure(variant)
+        b, x = a.new_vec(), a.new_vec()
+        b.upload(b_h)
+        for rep in range(2):                                     # the second solve replays the captured batch
+            x.fill(0.0)
+            st = smb.ConjugateGradient(tol, 2000, relative=True, single_reduce=True).solve_with_stats(a, b, x)
+            assert st["converged"], st
+            assert abs(int(st["iterations"]) - so["iterations"]) <= max(2, so["iterations"] // 50), (st, so["iterations"])
+            h = smb.ConjugateGradient.history(a.local)
+            assert h.size == st["iterations"]
+            k = min(20, h.size, so["history"].size)
+            assert np.allclose(h[:k], so["history"][:k], rtol=1e-9 if vdt == np.float64 else 1e-3)
+            got = x.to_numpy()
+            r = b_h.astype(np.float64) - orc.mvp(vals, cols, offs, got).astype(np.float64)
+            assert np.linalg.norm(r) / np.linalg.norm(b_h.astype(np.float64)) <= (10 * tol if vdt == np.float64 else 5e-3)
+            assert np.allclose(got, xo, rtol=0, atol=(1e-7 if vdt == np.float64 else 2e-2))
+        # the reference's loop on the same object afterwards: the workspace and the captured batch are keyed by the variant
+        x.fill(0.0)
+        st = smb.ConjugateGradient(tol, 2000, relative=True).solve_with_stats(a, b, x)
+        assert st["converged"] and abs(int(st["iterations"]) - so["iterations"]) <= max(2, so["iterations"] // 50)
+        assert np.allclose(x.to_numpy(), xo, rtol=0, atol=(1e-7 if vdt == np.float64 else 2e-2))
+    with pytest.raises(ValueError):
+        smb.ConjugateGradient(tol, 10, single_reduce=True).solve_with_stats(smb.SparseMatCRS.laplace(c, vdt, np.uint32, 4, 4, 4),
+                                                                           smb.DenseVec(c, 64, vdt), smb.DenseVec(c, 64, vdt))
+
+
 @pytest.mark.parametrize("vdt", [np.float64, np.float32])
 def test_cg_on_borrowed_misaligned_vectors(smb, orc, ctx, vdt):
     """b and x wrapped around caller memory one element past a 16-byte boundary (smb200_vec_wrap): the solver's fused

@@ -30,6 +30,7 @@ def _worker(rank, world, port, out_q, path):
         os.environ.setdefault("SMB200_P2P_TIMEOUT_MS", "20000")
         sys.path.insert(0, ROOT)
         sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import torch
         import torch.distributed as dist
 
         import cases
@@ -75,6 +76,16 @@ def _worker(rank, world, port, out_q, path):
             assert abs(int(st["iterations"]) - so["iterations"]) <= max(2, so["iterations"] // 50), (st, so["iterations"])
             assert st["final_residual"] <= rtol * np.linalg.norm(b_g.astype(np.float64)) * 1.0000001
             assert np.allclose(xs.to_numpy(), xo[lo:hi], rtol=0, atol=1e-7 if vdt == np.float64 else 2e-3)
+            # the single-reduction rearrangement (one all-reduce per iteration, cg_sr.cuh): same answer, same count +-2%
+            xs.fill(0.0)
+            st = smb.ConjugateGradient(rtol, 3000, relative=True, single_reduce=True).solve_with_stats(a, b, xs)
+            assert st["converged"], st
+            assert abs(int(st["iterations"]) - so["iterations"]) <= max(2, so["iterations"] // 50), (st, so["iterations"])
+            assert np.allclose(xs.to_numpy(), xo[lo:hi], rtol=0, atol=1e-7 if vdt == np.float64 else 2e-3)
+            rl = b_g[lo:hi].astype(np.float64) - a.mvp(xs).to_numpy().astype(np.float64)
+            rr = torch.tensor([float(rl @ rl)], dtype=torch.float64)
+            dist.all_reduce(rr)
+            assert float(rr.item()) ** 0.5 <= (10 * rtol if vdt == np.float64 else 5e-3) * np.linalg.norm(b_g.astype(np.float64))
 
         # ---- (2) general matrix: host ghost plan, packed sends, nnz-balanced bounds ---------------------------------
         vdt, idt = np.float64, np.uint64
