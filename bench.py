@@ -584,6 +584,17 @@ def run_ours(args):
                       "effective_gbs": Bcg * int(st["iterations"]) / (float(tms.item()) * 1e-3) / 1e9,
                       "frac_of_measured_hbm_peak": Bcg * int(st["iterations"]) / (float(tms.item()) * 1e-3) / 1e9 / (peak * world),
                       "final_residual": st["final_residual"]}
+        # the same iterations through the single-reduction loop (one all-reduce per iteration, smb200_dist_cg_solve_sr)
+        x0.fill(0.0)
+        smb.ConjugateGradient(1e-1, cg_iters, relative=True, single_reduce=True).solve_with_stats(a64, b, x0)
+        x0.fill(0.0)
+        barrier()
+        st = smb.ConjugateGradient(1e-30, cg_iters, single_reduce=True).solve_with_stats(a64, b, x0)
+        tms = torch.tensor([st["device_ms"]], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        line["cg"]["single_reduce"] = {"iterations": int(st["iterations"]), "device_ms": float(tms.item()),
+                                       "iter_per_s": int(st["iterations"]) / (float(tms.item()) * 1e-3),
+                                       "final_residual": st["final_residual"]}
     if not multi and not args.no_extras:
         a = x = y = None               # (already gone if the CG leg ran) free the C2 matrix before the larger extras
         line["extras"] = extras_single_gpu(smb, ctx, peak)

@@ -88,6 +88,15 @@ cg_ms = maxr(st["device_ms"])
 Bcg = nnz * 12 + (N + world) * 4 + 2 * N * 8 + 9 * N * 8
 out["cg_f64"] = {"iterations": int(st["iterations"]), "ms": cg_ms, "iter_per_s": st["iterations"] / cg_ms * 1e3,
                  "effective_gbs": Bcg * st["iterations"] / cg_ms / 1e6, "final_residual": st["final_residual"]}
+x0.fill(0.0)
+smb.ConjugateGradient(1e-1, iters, relative=True, single_reduce=True).solve_with_stats(a, b, x0)
+x0.fill(0.0)
+ctx.sync()
+dist.barrier()
+st = smb.ConjugateGradient(1e-30, iters, single_reduce=True).solve_with_stats(a, b, x0)
+sr_ms = maxr(st["device_ms"])
+out["cg_f64_single_reduce"] = {"iterations": int(st["iterations"]), "ms": sr_ms, "iter_per_s": st["iterations"] / sr_ms * 1e3,
+                               "final_residual": st["final_residual"]}
 if rank == 0:
     print(json.dumps(out), flush=True)
 dist.barrier()
