@@ -2,18 +2,21 @@
 // every scalar (alpha, beta, r.r, the stop test) kept on the device:
 //
 //   A  ap = A p,  pAp = p.ap                    SpMV with the dot fused into its epilogue (spmv.cu)
-//   B  x += (p*alpha); r -= (ap*alpha); rr' = r.r    alpha = rr / pAp computed by every thread
-//   C  stop test sqrt(rr') < threshold; p = (p*beta) + r   beta = rr' / rr
+//   B  r -= (ap*alpha); rr' = r.r                alpha = rr / pAp computed by every thread
+//   C  x += (p*alpha); stop test sqrt(rr') < threshold; p = (p*beta) + r   beta = rr' / rr
 //
 // Elementwise arithmetic is the reference's: product rounded, then add (two roundings, never an FMA),
-// alpha/beta are divisions in T.  Only the two reductions are re-ordered (fixed-order tree in f64).
-// Algorithmic bytes per iteration: SpMV bytes + 9*N*sizeof(T)  (B: x,p,r,ap in, x,r out; C: r,p in, p out)
+// alpha/beta are divisions in T.  Only the two reductions are re-ordered (fixed-order tree in f64).  The x update of
+// linearsolver.rs:45-46 rides kernel C instead of B (same operation on the same operands, p is read once per iteration
+// instead of twice).  Algorithmic bytes per iteration: SpMV bytes + 8*N*sizeof(T)  (B: r,ap in, r out; C: x,p,r in, x,p out)
 // against ~24*N*sizeof(T) plus 3-4 allocations in the reference's clone-heavy loop.
 //
 // Iterations are replayed from a CUDA graph in batches; the host only polls a pinned copy of the
 // (iteration, done) pair one batch behind the GPU, so the device never waits for the CPU.  After the
-// stop test fires the remaining kernels of a batch exit immediately, leaving x, r, p untouched — the
-// reference's `break` (linearsolver.rs:52-54).
+// stop test fires (in C, which has updated x first — the reference updates x before its `break`, linearsolver.rs:45-54)
+// the remaining kernels of a batch exit immediately, leaving x, r, p untouched.  Two flags: S_DONE is raised by one
+// thread of C while other CTAs of the same launch may still be starting, so C itself looks at S_DONE_SEEN, which the
+// next B raises when it finds S_DONE set.
 #include "common.cuh"
 #include "cg_sr.cuh"
 #include "halo.cuh"
@@ -30,7 +33,7 @@ namespace smb {
 // S_RR_LOCAL: multi-GPU only — the rank-local r.r, all-reduced OUT OF PLACE into S_RR_NEW (after the stop test
 // has fired the update kernels exit early and leave S_RR_LOCAL alone, so repeating the all-reduce is harmless).
 // S_RES2: Jacobi-preconditioned solves only — r.r for the stop test (S_RR / S_RR_NEW then hold r.z, z = D^-1 r).
-enum { S_RR = 0, S_PAP = 1, S_RR_NEW = 4, S_THRESH = 5, S_ITER = 6, S_DONE = 7, S_RR_LOCAL = 8, S_RES2 = 9, S_COUNT = 16 };
+enum { S_RR = 0, S_PAP = 1, S_RR_NEW = 4, S_THRESH = 5, S_ITER = 6, S_DONE = 7, S_RR_LOCAL = 8, S_RES2 = 9, S_DONE_SEEN = 13, S_COUNT = 16 };   // 10..12: cg_sr.cuh
 
 constexpr int kCgThreads = 256;
 
@@ -102,47 +105,45 @@ cg_init_kernel(const T* __restrict__ b, const T* __restrict__ ap, T* __restrict_
         if (threadIdx.x == 0) S[rr_slot] = (double)(T)total;
 }
 
-// B: x += (p * alpha); r -= (ap * alpha); S[RR_NEW] = r.r      (linearsolver.rs:45-51)
+// B: r -= (ap * alpha); S[RR_NEW] = r.r      (linearsolver.rs:47-51)
 //    PRE: S[RR_NEW] = r.(dinv * r) and S[RES2] = r.r
 template <class T, bool PRE>
 __global__ void __launch_bounds__(kCgThreads)
-cg_update_xr_kernel(T* __restrict__ x, T* __restrict__ r, const T* __restrict__ p, const T* __restrict__ ap, uint64_t n,
-                    double* __restrict__ S, int rr_slot, double* __restrict__ partials, unsigned int* __restrict__ ticket, int vec_ok,
-                    const T* __restrict__ dinv, const ArDev* __restrict__ ar) {
+cg_update_r_kernel(T* __restrict__ r, const T* __restrict__ ap, uint64_t n,
+                   double* __restrict__ S, int rr_slot, double* __restrict__ partials, unsigned int* __restrict__ ticket,
+                   const T* __restrict__ dinv, const ArDev* __restrict__ ar) {
     __shared__ double scratch[kCgThreads / 32 + 1];
     __shared__ double ar_sv[kMaxPeers][kArSlots], ar_in[kArSlots], ar_out[kArSlots];
-    if (__ldcg(S + S_DONE) != 0.0) return;
+    if (__ldcg(S + S_DONE) != 0.0) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) S[S_DONE_SEEN] = 1.0;
+        return;
+    }
     const T alpha = div_rn((T)__ldcg(S + S_RR), (T)(__ldcg(S + S_PAP) + __ldcg(S + S_PAP + 1) + __ldcg(S + S_PAP + 2)));
     using V = typename Vec16<T>::type;
     constexpr int N = Vec16<T>::N;
     const uint64_t tid = blockIdx.x * (uint64_t)kCgThreads + threadIdx.x;
     const uint64_t stride = (uint64_t)gridDim.x * kCgThreads;
-    const uint64_t nvec = vec_ok ? n / N : 0;      // a borrowed b / x (smb200_vec_wrap) may not be 16-byte aligned: element loop
+    const uint64_t nvec = n / N;
     T lane_acc[N], lane_acz[N];
 #pragma unroll
     for (int k = 0; k < N; ++k) lane_acc[k] = lane_acz[k] = T(0);
     for (uint64_t i = tid; i < nvec; i += stride) {
-        Pack16<T> px, pr, pp, pa, pd;
-        pp.v = __ldg(reinterpret_cast<const V*>(p) + i);
+        Pack16<T> pr, pa, pd;
         pa.v = __ldg(reinterpret_cast<const V*>(ap) + i);
         if constexpr (PRE) pd.v = __ldg(reinterpret_cast<const V*>(dinv) + i);
-        px.v = reinterpret_cast<V*>(x)[i];
         pr.v = reinterpret_cast<V*>(r)[i];
 #pragma unroll
         for (int k = 0; k < N; ++k) {
-            px.e[k] = add_rn(px.e[k], mul_rn(pp.e[k], alpha));
             pr.e[k] = sub_rn(pr.e[k], mul_rn(pa.e[k], alpha));
             lane_acc[k] = add_rn(lane_acc[k], mul_rn(pr.e[k], pr.e[k]));
             if constexpr (PRE) lane_acz[k] = add_rn(lane_acz[k], mul_rn(pr.e[k], mul_rn(pd.e[k], pr.e[k])));
         }
-        reinterpret_cast<V*>(x)[i] = px.v;
         reinterpret_cast<V*>(r)[i] = pr.v;
     }
     double acc = 0.0, acz = 0.0;
 #pragma unroll
     for (int k = 0; k < N; ++k) { acc += (double)lane_acc[k]; acz += (double)lane_acz[k]; }
     for (uint64_t i = nvec * N + tid; i < n; i += stride) {
-        x[i] = add_rn(x[i], mul_rn(p[i], alpha));
         const T rv = sub_rn(r[i], mul_rn(ap[i], alpha));
         r[i] = rv;
         acc += (double)mul_rn(rv, rv);
@@ -159,7 +160,7 @@ cg_update_xr_kernel(T* __restrict__ x, T* __restrict__ r, const T* __restrict__ 
         if (grid_sum<kCgThreads>(bsum, partials, ticket, scratch, total)) {
             if (ar != nullptr) {
                 // one rank per GPU: the CTA that finished last exchanges the ranks' r.r through peer memory (halo.cuh) and
-                // leaves the global value, rounded to T like the reference's scalar, where the p update expects it
+                // leaves the global value, rounded to T like the reference's scalar, where kernel C expects it
                 if (threadIdx.x == 0) ar_in[0] = total;
                 __syncthreads();
                 if (threadIdx.x < 32) ar_warp_allreduce(*ar, ar_in, ar_out, 1, ar_sv);
@@ -172,13 +173,15 @@ cg_update_xr_kernel(T* __restrict__ x, T* __restrict__ r, const T* __restrict__ 
     }
 }
 
-// C: stop test, bookkeeping, p = (p * beta) + r                  (linearsolver.rs:52-59)
+// C: x += (p * alpha); stop test, bookkeeping, p = (p * beta) + r          (linearsolver.rs:45-46, 52-59)
 //    PRE: the stop test looks at r.r (S[RES2]), beta = r.z' / r.z, p = (p * beta) + dinv * r
 template <class T, bool PRE>
 __global__ void __launch_bounds__(kCgThreads)
-cg_update_p_kernel(T* __restrict__ p, const T* __restrict__ r, uint64_t n, double* __restrict__ S,
-                   double* __restrict__ history, uint64_t hist_cap, const T* __restrict__ dinv) {
-    if (__ldcg(S + S_DONE) != 0.0) return;
+cg_update_xp_kernel(T* __restrict__ x, T* __restrict__ p, const T* __restrict__ r, uint64_t n, double* __restrict__ S,
+                    double* __restrict__ history, uint64_t hist_cap, int vec_ok, const T* __restrict__ dinv) {
+    if (__ldcg(S + S_DONE_SEEN) != 0.0) return;
+    const double rr_old = __ldcg(S + S_RR);
+    const T alpha = div_rn((T)rr_old, (T)(__ldcg(S + S_PAP) + __ldcg(S + S_PAP + 1) + __ldcg(S + S_PAP + 2)));    // as in B
     const double rr_new = __ldcg(S + S_RR_NEW);
     const double res = sqrt(PRE ? __ldcg(S + S_RES2) : rr_new);     // f64::sqrt(r_norm_squared.into())
     const bool done = res < __ldcg(S + S_THRESH);
@@ -188,25 +191,35 @@ cg_update_p_kernel(T* __restrict__ p, const T* __restrict__ r, uint64_t n, doubl
         S[S_ITER] = (double)(it + 1);
         if (done) S[S_DONE] = 1.0;
     }
-    if (done) return;
-    const T beta = div_rn((T)rr_new, (T)__ldcg(S + S_RR));
+    const T beta = done ? T(0) : div_rn((T)rr_new, (T)rr_old);
     using V = typename Vec16<T>::type;
     constexpr int N = Vec16<T>::N;
     const uint64_t tid = blockIdx.x * (uint64_t)kCgThreads + threadIdx.x;
     const uint64_t stride = (uint64_t)gridDim.x * kCgThreads;
-    const uint64_t nvec = n / N;
+    const uint64_t nvec = vec_ok ? n / N : 0;      // a borrowed x (smb200_vec_wrap) may not be 16-byte aligned: element loop
     for (uint64_t i = tid; i < nvec; i += stride) {
-        Pack16<T> pp, pr, pd;
+        Pack16<T> px, pp, pr, pd;
         pp.v = reinterpret_cast<V*>(p)[i];
-        pr.v = __ldg(reinterpret_cast<const V*>(r) + i);
-        if constexpr (PRE) pd.v = __ldg(reinterpret_cast<const V*>(dinv) + i);
+        px.v = reinterpret_cast<V*>(x)[i];
+        if (!done) {
+            pr.v = __ldg(reinterpret_cast<const V*>(r) + i);
+            if constexpr (PRE) pd.v = __ldg(reinterpret_cast<const V*>(dinv) + i);
+        }
 #pragma unroll
-        for (int k = 0; k < N; ++k) pp.e[k] = add_rn(mul_rn(pp.e[k], beta), PRE ? mul_rn(pd.e[k], pr.e[k]) : pr.e[k]);
-        reinterpret_cast<V*>(p)[i] = pp.v;
+        for (int k = 0; k < N; ++k) px.e[k] = add_rn(px.e[k], mul_rn(pp.e[k], alpha));
+        reinterpret_cast<V*>(x)[i] = px.v;
+        if (!done) {
+#pragma unroll
+            for (int k = 0; k < N; ++k) pp.e[k] = add_rn(mul_rn(pp.e[k], beta), PRE ? mul_rn(pd.e[k], pr.e[k]) : pr.e[k]);
+            reinterpret_cast<V*>(p)[i] = pp.v;
+        }
     }
-    for (uint64_t i = nvec * N + tid; i < n; i += stride) p[i] = add_rn(mul_rn(p[i], beta), PRE ? mul_rn(dinv[i], r[i]) : r[i]);
+    for (uint64_t i = nvec * N + tid; i < n; i += stride) {
+        const T pv = p[i];
+        x[i] = add_rn(x[i], mul_rn(pv, alpha));
+        if (!done) p[i] = add_rn(mul_rn(pv, beta), PRE ? mul_rn(dinv[i], r[i]) : r[i]);
+    }
 }
-
 
 // ---- single-reduction variant (cg_sr.cuh) ------------------------------------------------------------
 // U: p = r + (p * beta); s = w + (s * beta); x += (p * alpha); r -= (s * alpha); S[RR_NEW] = r.r of this rank (f64, unrounded)
@@ -339,27 +352,27 @@ smb200_status cg_init_launch(smb200_ctx* ctx, CgWork& w, int vt, const void* b, 
     return SMB200_OK;
 }
 
-smb200_status cg_xr_launch(smb200_ctx* ctx, CgWork& w, int vt, void* x, uint64_t n, const void* dinv, const ArDev* ar) {
+smb200_status cg_r_launch(smb200_ctx* ctx, CgWork& w, int vt, uint64_t n, const void* dinv, const ArDev* ar) {
     const unsigned g = cg_grid(ctx, n, vt);
     const int slot = ctx->world > 1 ? S_RR_LOCAL : S_RR_NEW;
-    const int vec_ok = ((uintptr_t)x & 15u) == 0 ? 1 : 0;
     if (dinv) {
-        if (vt == SMB200_F64) cg_update_xr_kernel<double, true><<<g, kCgThreads, 0, ctx->stream>>>((double*)x, (double*)w.r, (const double*)w.p, (const double*)w.ap, n, w.scalars, slot, ctx->red_partials, ctx->red_ticket, vec_ok, (const double*)dinv, nullptr);
-        else cg_update_xr_kernel<float, true><<<g, kCgThreads, 0, ctx->stream>>>((float*)x, (float*)w.r, (const float*)w.p, (const float*)w.ap, n, w.scalars, slot, ctx->red_partials, ctx->red_ticket, vec_ok, (const float*)dinv, nullptr);
-    } else if (vt == SMB200_F64) cg_update_xr_kernel<double, false><<<g, kCgThreads, 0, ctx->stream>>>((double*)x, (double*)w.r, (const double*)w.p, (const double*)w.ap, n, w.scalars, slot, ctx->red_partials, ctx->red_ticket, vec_ok, nullptr, ar);
-    else cg_update_xr_kernel<float, false><<<g, kCgThreads, 0, ctx->stream>>>((float*)x, (float*)w.r, (const float*)w.p, (const float*)w.ap, n, w.scalars, slot, ctx->red_partials, ctx->red_ticket, vec_ok, nullptr, ar);
+        if (vt == SMB200_F64) cg_update_r_kernel<double, true><<<g, kCgThreads, 0, ctx->stream>>>((double*)w.r, (const double*)w.ap, n, w.scalars, slot, ctx->red_partials, ctx->red_ticket, (const double*)dinv, nullptr);
+        else cg_update_r_kernel<float, true><<<g, kCgThreads, 0, ctx->stream>>>((float*)w.r, (const float*)w.ap, n, w.scalars, slot, ctx->red_partials, ctx->red_ticket, (const float*)dinv, nullptr);
+    } else if (vt == SMB200_F64) cg_update_r_kernel<double, false><<<g, kCgThreads, 0, ctx->stream>>>((double*)w.r, (const double*)w.ap, n, w.scalars, slot, ctx->red_partials, ctx->red_ticket, nullptr, ar);
+    else cg_update_r_kernel<float, false><<<g, kCgThreads, 0, ctx->stream>>>((float*)w.r, (const float*)w.ap, n, w.scalars, slot, ctx->red_partials, ctx->red_ticket, nullptr, ar);
     count_launch();
     SMB_CUDA(cudaGetLastError());
     return SMB200_OK;
 }
 
-smb200_status cg_p_launch(smb200_ctx* ctx, CgWork& w, int vt, uint64_t n, const void* dinv) {
+smb200_status cg_xp_launch(smb200_ctx* ctx, CgWork& w, int vt, void* x, uint64_t n, const void* dinv) {
     const unsigned g = cg_grid(ctx, n, vt);
+    const int vec_ok = ((uintptr_t)x & 15u) == 0 ? 1 : 0;
     if (dinv) {
-        if (vt == SMB200_F64) cg_update_p_kernel<double, true><<<g, kCgThreads, 0, ctx->stream>>>((double*)w.p, (const double*)w.r, n, w.scalars, w.history, w.hist_cap, (const double*)dinv);
-        else cg_update_p_kernel<float, true><<<g, kCgThreads, 0, ctx->stream>>>((float*)w.p, (const float*)w.r, n, w.scalars, w.history, w.hist_cap, (const float*)dinv);
-    } else if (vt == SMB200_F64) cg_update_p_kernel<double, false><<<g, kCgThreads, 0, ctx->stream>>>((double*)w.p, (const double*)w.r, n, w.scalars, w.history, w.hist_cap, nullptr);
-    else cg_update_p_kernel<float, false><<<g, kCgThreads, 0, ctx->stream>>>((float*)w.p, (const float*)w.r, n, w.scalars, w.history, w.hist_cap, nullptr);
+        if (vt == SMB200_F64) cg_update_xp_kernel<double, true><<<g, kCgThreads, 0, ctx->stream>>>((double*)x, (double*)w.p, (const double*)w.r, n, w.scalars, w.history, w.hist_cap, vec_ok, (const double*)dinv);
+        else cg_update_xp_kernel<float, true><<<g, kCgThreads, 0, ctx->stream>>>((float*)x, (float*)w.p, (const float*)w.r, n, w.scalars, w.history, w.hist_cap, vec_ok, (const float*)dinv);
+    } else if (vt == SMB200_F64) cg_update_xp_kernel<double, false><<<g, kCgThreads, 0, ctx->stream>>>((double*)x, (double*)w.p, (const double*)w.r, n, w.scalars, w.history, w.hist_cap, vec_ok, nullptr);
+    else cg_update_xp_kernel<float, false><<<g, kCgThreads, 0, ctx->stream>>>((float*)x, (float*)w.p, (const float*)w.r, n, w.scalars, w.history, w.hist_cap, vec_ok, nullptr);
     count_launch();
     SMB_CUDA(cudaGetLastError());
     return SMB200_OK;
@@ -397,8 +410,8 @@ static smb200_status cg_iteration(smb200_crs* a, void* x, const void* dinv) {
     smb200_ctx* ctx = a->ctx;
     CgWork& w = a->cg;
     SMB_TRY(spmv_launch_cg(a, a->plan, 0, a->n_rows, w.p, w.ap, w.p, w.scalars, 0, true));
-    SMB_TRY(cg_xr_launch(ctx, w, a->vt, x, a->n_rows, dinv));
-    SMB_TRY(cg_p_launch(ctx, w, a->vt, a->n_rows, dinv));
+    SMB_TRY(cg_r_launch(ctx, w, a->vt, a->n_rows, dinv));
+    SMB_TRY(cg_xp_launch(ctx, w, a->vt, x, a->n_rows, dinv));
     return SMB200_OK;
 }
 
@@ -496,7 +509,7 @@ smb200_status cg_solve_impl(smb200_crs* a, const smb200_vec* b, smb200_vec* x, d
                 }
                 e = cudaGraphLaunch(w.graph, ctx->stream);
                 if (e != cudaSuccess) { set_error("cg_solve: graph launch failed: %s", cudaGetErrorString(e)); st = SMB200_ERR_CUDA; break; }
-                count_launch(4 * (uint64_t)batch);   // SpMV+dot, dot finalize, x/r update, p update
+                count_launch(4 * (uint64_t)batch);   // SpMV+dot, dot finalize, r update, x/p update
             } else {
                 for (uint64_t k = 0; k < nb && st == SMB200_OK; ++k) st = cg_iteration(a, x->d, dinv);
                 if (st != SMB200_OK) break;

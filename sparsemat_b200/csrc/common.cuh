@@ -263,8 +263,8 @@ smb200_status cg_init_launch(smb200_ctx* ctx, CgWork& w, int vt, const void* b, 
 smb200_status cgsr_prepare(smb200_ctx* ctx, CgWork& w, int vt);
 smb200_status cgsr_update_launch(smb200_ctx* ctx, CgWork& w, int vt, void* x, uint64_t n);
 smb200_status cgsr_scalar_launch(smb200_ctx* ctx, CgWork& w, int vt, const ArDev* ar);
-smb200_status cg_xr_launch(smb200_ctx* ctx, CgWork& w, int vt, void* x, uint64_t n, const void* dinv = nullptr, const ArDev* ar = nullptr);
-smb200_status cg_p_launch(smb200_ctx* ctx, CgWork& w, int vt, uint64_t n, const void* dinv = nullptr);
+smb200_status cg_r_launch(smb200_ctx* ctx, CgWork& w, int vt, uint64_t n, const void* dinv = nullptr, const ArDev* ar = nullptr);
+smb200_status cg_xp_launch(smb200_ctx* ctx, CgWork& w, int vt, void* x, uint64_t n, const void* dinv = nullptr);
 smb200_status cg_solve_impl(smb200_crs* a, const smb200_vec* b, smb200_vec* x, double tol, int32_t relative,
                             uint64_t iter_max, smb200_cg_stats* stats, const void* dinv);
 

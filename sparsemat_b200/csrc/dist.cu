@@ -934,11 +934,11 @@ static smb200_status dist_cg_impl(smb200_dist* d, const smb200_vec* b, smb200_ve
     smb200_status st = SMB200_OK;
     uint64_t launched = 0, rounds = 0;
     bool finished = false;
-    // One iteration: halo exchange + SpMV with p.Ap fused (three launches) | all-reduce | x, r update + r.r | all-reduce | p update.
+    // One iteration: halo exchange + SpMV with p.Ap fused (three launches) | all-reduce | r update + r.r | all-reduce | x, p update.
     // Every rank runs the same sequence: the stop flag derives from all-reduced values, hence is identical everywhere, and
     // iterations past it exit early on the device.
     // With the ring kernel as the local product (ONE launch, one p.Ap slot) the two all-reduces ride inside the kernels that
-    // produce their operands — the fused dot's finalize kernel and the last CTA of the x / r update — so a distributed
+    // produce their operands — the fused dot's finalize kernel and the last CTA of the r update — so a distributed
     // iteration is the same four launches as a single-GPU one.  Other local plans keep the two 1-CTA all-reduce kernels.
     const bool fused_ar = multi && d->p2p && dist_exchanges(d) && a->plan.built && a->plan.variant == SMB200_SPMV_RING;
     auto iteration = [&]() -> smb200_status {
@@ -948,9 +948,9 @@ static smb200_status dist_cg_impl(smb200_dist* d, const smb200_vec* b, smb200_ve
         g_dot_ar = nullptr;
         SMB_TRY(sp);
         if (multi && !fused_ar) SMB_TRY(dist_allreduce(d, S + S_PAP, S + S_PAP, 3, false));
-        SMB_TRY(cg_xr_launch(ctx, w, d->vt, x->d, n, nullptr, fused_ar ? d->ar_dev : nullptr));
+        SMB_TRY(cg_r_launch(ctx, w, d->vt, n, nullptr, fused_ar ? d->ar_dev : nullptr));
         if (multi && !fused_ar) SMB_TRY(dist_allreduce(d, S + S_RR_LOCAL, S + S_RR_NEW, 1, f32));     // r.r is a T in the reference: rounded like the single-GPU path
-        return cg_p_launch(ctx, w, d->vt, n);
+        return cg_xp_launch(ctx, w, d->vt, x->d, n);
     };
     // Single-reduction iteration (cg_sr.cuh): vector update with the rank's r.r | halo exchange + w = A r with w.r fused |
     // ONE all-reduce of the pair + the scalar step — inside the fused dot's finalize kernel when the product is one launch

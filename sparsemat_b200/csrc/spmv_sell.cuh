@@ -21,7 +21,7 @@ struct alignas(16) SellBlock {            // one per row block; the producer loa
     unsigned long long r0;                // first row of the block
     unsigned rows, n_slices;              // rows, slices of 32 rows
     unsigned e_bytes;                     // padded entries of the block (= bytes of codes; positions take twice as much)
-    unsigned flags;                       // kSellGhost: a window reaches past g0 (distributed plans)
+    unsigned flags;                       // kSellGhost: a window reaches past g0 (distributed plans); kSellSelf + position << 8: see below
     unsigned long long ebase;             // first padded entry of the block in s_codes / s_cols (a multiple of 32)
     unsigned long long rbase;             // first row-length byte (a multiple of 16)
     unsigned long long sbase;             // first slice-offset word (a multiple of 4)
@@ -30,10 +30,15 @@ struct alignas(16) SellBlock {            // one per row block; the producer loa
 };
 static_assert(sizeof(SellBlock) == 96, "SellBlock layout");
 constexpr unsigned kSellGhost = 1u;
+// kSellSelf: one staged x window covers the block's own rows [r0, r0 + rows) as columns; flags >> 8 is the element position
+// of x[r0] inside the staged windows.  The fused dot x.(A x) of a CG iteration then takes its weight from shared memory
+// instead of reading x a second time from HBM.
+constexpr unsigned kSellSelf = 2u;
 
 struct SellDesc {                          // what the consumers need of a staged block
     unsigned long long r0;
     unsigned rows, n_slices;
+    unsigned self_pos;                     // position of x[r0] in the staged windows, ~0u: not staged
 };
 
 // ---- plan time -----------------------------------------------------------------------------------------------------
@@ -93,11 +98,14 @@ sell_fill_kernel(const I* __restrict__ offs, const I* __restrict__ blk_rows, con
         sb.r0 = r0; sb.rows = rows; sb.n_slices = n_slices; sb.e_bytes = run;
         sb.ebase = ebase[b]; sb.rbase = rbase[b]; sb.sbase = sbase[b];
         bool ghost = false;
+        unsigned at = 0, self = ~0u;
         for (int i = 0; i < kNSeg; ++i) {
             sb.lo[i] = seg_lo[kNSeg * b + i]; sb.len[i] = seg_len[kNSeg * b + i];
             ghost = ghost || (sb.len[i] != 0u && sb.lo[i] + sb.len[i] > g0);
+            if (self == ~0u && sb.len[i] != 0u && sb.lo[i] <= r0 && r1 <= sb.lo[i] + sb.len[i] && r1 <= g0) self = at + (unsigned)(r0 - sb.lo[i]);
+            at += sb.len[i];
         }
-        sb.flags = ghost ? kSellGhost : 0u;
+        sb.flags = (ghost ? kSellGhost : 0u) | (self != ~0u && self < (1u << 24) ? kSellSelf | (self << 8) : 0u);
         blocks[b] = sb;
     }
     __syncthreads();
@@ -182,6 +190,7 @@ spmv_ring_sell_kernel(const SellBlock* __restrict__ blocks, const uint8_t* __res
                 if (j >= stages) mbar_wait(&empty[s], parity ^ 1u);
                 unsigned char* base = smem_raw + (size_t)s * stage_bytes;
                 s_desc[s].r0 = h0.x; s_desc[s].rows = rows; s_desc[s].n_slices = n_slices;
+                if constexpr (DOT) s_desc[s].self_pos = (flags & kSellSelf) != 0u && dot.w == (const void*)x ? flags >> 8 : ~0u;
                 if constexpr (DIST) {
                     if (!waited && ((flags & kSellGhost) != 0u || (blockIdx.x == 0 && j + 1 == n_my))) {
                         halo_wait(halo, epoch);
@@ -240,7 +249,7 @@ spmv_ring_sell_kernel(const SellBlock* __restrict__ blocks, const uint8_t* __res
                 const unsigned off = so[q], w = (so[q + 1] - off) >> 5;
                 const unsigned len = live ? (unsigned)sl[row] : 0u;
                 T wv = T(0);
-                if constexpr (DOT) { if (live) wv = __ldg((const T*)dot.w + d.r0 + row); }
+                if constexpr (DOT) { if (live) wv = d.self_pos != ~0u ? sx[d.self_pos + row] : __ldg((const T*)dot.w + d.r0 + row); }
                 T sum = T(0);
                 const uint8_t* pc = sc + off + lane;
                 const uint16_t* pp = sp + off + lane;
