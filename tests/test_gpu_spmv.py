@@ -349,7 +349,7 @@ def test_small_matrix_sweep_all_variants_types_and_entry_points():
 
 @pytest.mark.parametrize("vdt,idt", COMBOS)
 def test_bandsplit_column_bands(smb, orc, ctx, vdt, idt):
-    """BANDSPLIT (experimental, opt-in): the matrix is cut into column bands at plan time and multiplied band by band, the
+    """BANDSPLIT (AUTO picks it when x is far larger than L2 and the columns have no locality; forced here): the matrix is cut into column bands at plan time and multiplied band by band, the
     first launch writing y and the others adding to it.  Tiny bands are forced here so that small matrices split into many.
     Band-major row sums: within the north-star tolerance of the oracle (not bit-exact); a row whose entries all fall into one
     band IS bit-exact; fused dot and CG ride the last band."""
