@@ -95,3 +95,45 @@ def test_vector_kernels_against_python_restatement(orc, vdt):
     assert np.array_equal(z[:100], x[:100] + y[:100]) and np.array_equal(z[100:], x[100:])
     with pytest.raises(orc.OraclePanic):
         orc.vec_sub(z[:10].copy(), y)                                                 # "Dimension mismatch" (densevec.rs:61-63)
+
+
+def test_single_reduction_recurrences_against_the_oracle_solver(orc):
+    """The scalar recurrences of the single-reduction loop (sparsemat_b200/csrc/cg_sr.cuh: beta = g'/g, alpha = g'/(d - beta g'/alpha),
+    p = r + beta p, s = w + beta s, x += alpha p, r -= alpha s, with g' = r.r and d = (A r).r taken behind ONE product) restated in
+    numpy and run beside the oracle's ConjugateGradient::solve (linearsolver.rs:27-61) on a 3-D Laplacian: same residual
+    history over the first iterations, same iteration count within 2 %, same solution.  Guards the algebra the CUDA kernels
+    implement; their own parity tests are tests/test_gpu_cg_tocrs.py::test_single_reduction_* and tests/test_gpu_dist.py."""
+    n = 14
+    N = n ** 3
+    vals, cols, offs = orc.laplace(np.float64, np.uint32, n, n, n)
+    b = orc.mvp(vals, cols, offs, orc.uniform(np.float64, 6, N))
+    tol = 1e-10
+    xo = np.zeros(N)
+    so = orc.cg(N, N, vals, cols, offs, b, xo, tol=tol, relative=True, iter_max=1000, history_cap=1000)
+    assert so["converged"]
+    thresh = tol * float(np.sqrt(b @ b))
+    A = lambda v: orc.mvp(vals, cols, offs, np.ascontiguousarray(v))  # noqa: E731
+    x = np.zeros(N)
+    r = b - A(x)
+    w = A(r)
+    g, d = float(r @ r), float(w @ r)
+    alpha, beta = g / d, 0.0
+    p, s = np.zeros(N), np.zeros(N)
+    hist = []
+    for _ in range(1000):
+        p = r + beta * p
+        s = w + beta * s
+        x = x + alpha * p
+        r = r - alpha * s
+        w = A(r)
+        gn, d = float(r @ r), float(w @ r)
+        hist.append(np.sqrt(gn))
+        if hist[-1] < thresh:
+            break
+        beta = gn / g
+        alpha = gn / (d - beta * gn / alpha)
+        g = gn
+    assert abs(len(hist) - so["iterations"]) <= max(2, so["iterations"] // 50), (len(hist), so["iterations"])
+    k = min(20, len(hist), so["history"].size)
+    assert np.allclose(hist[:k], so["history"][:k], rtol=1e-9)
+    assert np.allclose(x, xo, rtol=0, atol=1e-8)
