@@ -334,7 +334,7 @@ smb200_status cg_prepare(smb200_ctx* ctx, CgWork& w, int vt, uint64_t n, uint64_
         SMB_CUDA(cudaMalloc(&w.history, w.hist_cap * sizeof(double)));
         w.n = n;
     }
-    SMB_TRY(ensure_reduction_scratch(ctx, (size_t)ctx->sm_count * 16 + 16));     // two partials per CTA (preconditioned x/r update)
+    SMB_TRY(ensure_reduction_scratch(ctx, (size_t)ctx->sm_count * 16 + 16));     // two partials per CTA (preconditioned r update)
     return SMB200_OK;
 }
 

@@ -65,7 +65,7 @@ def test_jacobi_pcg_against_numpy_and_plain_cg(smb, orc, ctx):
     st = smb.JacobiPCG(tol, 2000).solve_with_stats(a, smb.DenseVec.from_vec(ctx, b), x)
     it_np = _numpy_pcg(a_sp, b, np.zeros(n), tol, 2000)
     assert st["converged"] and abs(int(st["iterations"]) - it_np) <= 3, (st, it_np)
-    # fused like cg.cu: four launches per iteration (SpMV + p.Ap, its finalize, x / r update, p update), replayed from a graph
+    # fused like cg.cu: four launches per iteration (SpMV + p.Ap, its finalize, r update, x / p update), replayed from a graph
     # in batches of 8 that may overrun the stop by two batches; no per-iteration host round trip
     assert int(st["launches"]) <= 4 * (int(st["iterations"]) + 16) + 24, st
     got = x.to_numpy()
